@@ -1,0 +1,51 @@
+// C-ABI entry points for convolution: validation + routing between the tcgen05 implicit-GEMM kernels
+// (conv_umma.cu) and the shape-complete SIMT kernels (conv_simt.cu).
+#include "common.cuh"
+
+namespace sgb {
+int conv_forward_simt(const sgb_conv_desc* d, const void* x, const void* w, void* y, cudaStream_t s);
+int conv_wgrad_simt(const sgb_conv_desc* d, const void* x, const void* dy, void* dw, cudaStream_t s);
+bool conv_umma_eligible(const sgb_conv_desc* d);
+int conv_forward_umma(const sgb_conv_desc* d, const void* x, const void* w, void* y, cudaStream_t s);
+
+static int validate(const sgb_conv_desc* d) {
+  SGB_REQUIRE(d != nullptr, "descriptor is NULL");
+  SGB_REQUIRE(d->dtype >= SGB_F32 && d->dtype <= SGB_F64, "unsupported dtype");
+  SGB_REQUIRE(d->n >= 0 && d->ci >= 1 && d->co >= 1, "bad channel / batch counts");
+  SGB_REQUIRE(d->groups >= 1 && d->ci % d->groups == 0 && d->co % d->groups == 0, "channels must divide into groups");
+  SGB_REQUIRE(d->kh >= 1 && d->kw >= 1 && d->stride >= 1, "bad kernel size / stride");
+  SGB_REQUIRE(d->pad_y >= 0 && d->pad_x >= 0, "padding must be non-negative");
+  SGB_REQUIRE(d->in_h >= 1 && d->in_w >= 1 && d->out_h >= 1 && d->out_w >= 1, "bad spatial size");
+  if (!d->transposed) {
+    SGB_REQUIRE((d->out_h - 1) * d->stride + d->kh - 2 * d->pad_y <= d->in_h &&
+                (d->out_w - 1) * d->stride + d->kw - 2 * d->pad_x <= d->in_w, "output larger than the input allows");
+  } else {
+    SGB_REQUIRE(d->out_h >= (d->in_h - 1) * d->stride + d->kh - 2 * d->pad_y &&
+                d->out_w >= (d->in_w - 1) * d->stride + d->kw - 2 * d->pad_x, "transposed output smaller than the input needs");
+  }
+  return 0;
+}
+}  // namespace sgb
+
+using namespace sgb;
+
+extern "C" int sgb_conv2d_uses_tensor_cores(const sgb_conv_desc* d) {
+  return (d && conv_umma_eligible(d)) ? 1 : 0;
+}
+
+extern "C" int sgb_conv2d_forward(const sgb_conv_desc* d, const void* x, const void* w, void* y, void* stream) {
+  if (int r = validate(d)) return r;
+  if ((int64_t)d->n * d->out_h * d->out_w == 0) return 0;
+  SGB_REQUIRE(x && w && y, "x, w and y must not be NULL");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (conv_umma_eligible(d)) return conv_forward_umma(d, x, w, y, s);
+  return conv_forward_simt(d, x, w, y, s);
+}
+
+extern "C" int sgb_conv2d_wgrad(const sgb_conv_desc* d, const void* x, const void* dy, void* dw, void* stream) {
+  if (int r = validate(d)) return r;
+  SGB_REQUIRE(!d->transposed, "wgrad takes the non-transposed description (swap x and dy for conv_transpose2d)");
+  SGB_REQUIRE(dw, "dw must not be NULL");
+  SGB_REQUIRE((x && dy) || (int64_t)d->n == 0, "x and dy must not be NULL");
+  return conv_wgrad_simt(d, x, dy, dw, (cudaStream_t)stream);
+}

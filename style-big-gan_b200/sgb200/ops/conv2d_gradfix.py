@@ -1,0 +1,220 @@
+"""conv2d / conv_transpose2d with gradients of arbitrary order, on the libsgb200 convolution kernels.
+
+Public interface of the reference's `stylegan2ada/torch_utils/ops/conv2d_gradfix.py`: `conv2d` (:33),
+`conv_transpose2d` (:38), the `no_weight_gradients()` context manager (:25-31) and the module attributes
+`enabled` / `weight_gradients_disabled` (:22-23) that `train_parts/regularizations.py:27,48` and
+`trainers.py:512` touch.  As in the reference, the backward of a convolution is the *other* convolution
+(data gradient) plus a weight-gradient op whose own backward is two more convolutions (:119-165), which is
+what makes R1 / path-length double backward work.
+
+Extensions used by our own conv2d_resample / modulated_conv2d (keyword-only, default off):
+  flip_weight=False   use the spatially flipped kernel without materialising w.flip([2, 3])
+  in_scale=[N,Ci]     multiply x by a per-sample per-channel scale while it is loaded (style modulation)
+"""
+import contextlib
+
+import torch
+
+from .. import _lib
+
+enabled = True                      # kept for API compatibility; the custom op is the only implementation
+weight_gradients_disabled = False   # forcefully disable computation of gradients with respect to the weights
+
+
+@contextlib.contextmanager
+def no_weight_gradients():
+    global weight_gradients_disabled
+    old = weight_gradients_disabled
+    weight_gradients_disabled = True
+    yield
+    weight_gradients_disabled = old
+
+
+def conv2d(input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1, *, flip_weight=False, in_scale=None):
+    _lib.require_cuda(input, 'input')
+    op = _conv2d_op(transpose=False, weight_shape=weight.shape, stride=stride, padding=padding, output_padding=0,
+                    dilation=dilation, groups=groups, flip=bool(flip_weight))
+    return op.apply(input, weight, bias, in_scale)
+
+
+def conv_transpose2d(input, weight, bias=None, stride=1, padding=0, output_padding=0, groups=1, dilation=1, *,
+                     flip_weight=False, in_scale=None):
+    _lib.require_cuda(input, 'input')
+    op = _conv2d_op(transpose=True, weight_shape=weight.shape, stride=stride, padding=padding,
+                    output_padding=output_padding, dilation=dilation, groups=groups, flip=bool(flip_weight))
+    return op.apply(input, weight, bias, in_scale)
+
+
+def _pair(xs):
+    xs = tuple(xs) if isinstance(xs, (tuple, list)) else (xs, xs)
+    assert len(xs) == 2 and all(isinstance(x, int) for x in xs)
+    return xs
+
+
+def _make_desc(x, y, transposed, ci, co, kh, kw, stride, pad, groups, flip, in_scale=None, bias=None):
+    d = _lib.ConvDesc()
+    d.dtype = _lib.dtype_code(x)
+    d.transposed = int(transposed)
+    d.n, d.ci, d.co = x.shape[0], ci, co
+    d.in_h, d.in_w, d.out_h, d.out_w = x.shape[2], x.shape[3], y.shape[2], y.shape[3]
+    d.kh, d.kw, d.stride, d.pad_y, d.pad_x, d.groups, d.flip = kh, kw, stride, pad[0], pad[1], groups, int(flip)
+    d.x_strides = _lib.strides4(x)
+    d.y_strides = _lib.strides4(y)
+    d.in_scale = _lib.ptr(in_scale)
+    d.out_scale = None
+    d.noise = None
+    d.bias = _lib.ptr(bias)
+    d.act = 1 if bias is not None else 0       # linear, gain 1, no clamp == plain bias add
+    d.alpha, d.gain, d.clamp = 0.0, 1.0, -1.0
+    return d
+
+
+def _scale_arg(in_scale, x):
+    if in_scale is None:
+        return None
+    assert in_scale.shape == (x.shape[0], x.shape[1])
+    return in_scale.detach().to(_lib.acc_dtype(x.dtype)).contiguous()
+
+
+_cache = dict()
+
+
+def _conv2d_op(transpose, weight_shape, stride, padding, output_padding, dilation, groups, flip):
+    weight_shape = tuple(int(s) for s in weight_shape)
+    stride = _pair(stride)
+    padding = _pair(padding)
+    output_padding = _pair(output_padding)
+    dilation = _pair(dilation)
+    key = (transpose, weight_shape, stride, padding, output_padding, dilation, groups, flip)
+    if key in _cache:
+        return _cache[key]
+
+    assert groups >= 1 and len(weight_shape) == 4
+    if stride[0] != stride[1]:
+        raise NotImplementedError('sgb200 conv: stride must be the same in both directions')
+    if dilation != (1, 1):
+        raise NotImplementedError('sgb200 conv: dilation is not supported')
+    assert all(p >= 0 for p in padding)
+    if not transpose:
+        assert output_padding == (0, 0)
+    else:
+        assert all(0 <= output_padding[i] < max(stride[i], dilation[i]) for i in range(2))
+    s = stride[0]
+    kh, kw = weight_shape[2], weight_shape[3]
+    # channel counts of the op's input / output
+    if not transpose:
+        co, ci = weight_shape[0], weight_shape[1] * groups
+    else:
+        ci, co = weight_shape[0], weight_shape[1] * groups
+
+    def out_hw(ih, iw):
+        if not transpose:
+            return (ih + 2 * padding[0] - kh) // s + 1, (iw + 2 * padding[1] - kw) // s + 1
+        return (ih - 1) * s - 2 * padding[0] + kh + output_padding[0], (iw - 1) * s - 2 * padding[1] + kw + output_padding[1]
+
+    def calc_output_padding(input_shape, output_shape):
+        if transpose:
+            return [0, 0]
+        return [input_shape[i + 2] - (output_shape[i + 2] - 1) * s - (1 - 2 * padding[i]) - (weight_shape[i + 2] - 1)
+                for i in range(2)]
+
+    class Conv2d(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, input, weight, bias, in_scale):
+            assert tuple(weight.shape) == weight_shape
+            if input.ndim != 4 or input.shape[1] != ci:
+                raise RuntimeError(f'conv: expected input [N, {ci}, H, W], got {tuple(input.shape)}')
+            if weight.dtype != input.dtype:
+                raise RuntimeError('conv: weight and input must have the same dtype')
+            w = weight.contiguous()
+            oh, ow = out_hw(input.shape[2], input.shape[3])
+            if oh < 1 or ow < 1:
+                raise RuntimeError('conv: output would be empty')
+            y = torch.empty([input.shape[0], co, oh, ow], dtype=input.dtype, device=input.device,
+                            memory_format=_lib.out_format(input))
+            sc = _scale_arg(in_scale, input)
+            b = bias.contiguous() if bias is not None else None
+            if y.numel() > 0:
+                d = _make_desc(input, y, transpose, ci, co, kh, kw, s, padding, groups, flip, sc, b)
+                with torch.cuda.device(input.device):
+                    rc = _lib.lib().sgb_conv2d_forward(d, _lib.ptr(input), _lib.ptr(w), _lib.ptr(y), _lib.stream_ptr(input.device))
+                _lib.check(rc, 'conv2d_forward')
+            ctx.save_for_backward(input, weight, in_scale)
+            ctx.has_bias = bias is not None
+            return y
+
+        @staticmethod
+        def backward(ctx, grad_output):
+            input, weight, in_scale = ctx.saved_tensors
+            grad_input = grad_weight = grad_bias = grad_scale = None
+            need_x = ctx.needs_input_grad[0]
+            need_s = in_scale is not None and ctx.needs_input_grad[3]
+            if need_x or need_s:
+                p = calc_output_padding(input.shape, grad_output.shape)
+                dgrad = _conv2d_op(transpose=(not transpose), weight_shape=weight_shape, stride=stride, padding=padding,
+                                   output_padding=p, dilation=dilation, groups=groups, flip=flip)
+                g = dgrad.apply(grad_output, weight, None, None)        # gradient wrt (input * in_scale)
+                assert g.shape == input.shape
+                if in_scale is None:
+                    grad_input = g
+                else:
+                    from . import fma as _fma
+                    if need_x:
+                        grad_input = _fma.scale_nc(g, in_scale)
+                    if need_s:
+                        grad_scale = _fma.mul_sum_hw(g, input).to(in_scale.dtype)
+            if ctx.needs_input_grad[1] and not weight_gradients_disabled:
+                grad_weight = Conv2dGradWeight.apply(grad_output, input, in_scale)
+                assert tuple(grad_weight.shape) == weight_shape
+            if ctx.has_bias and ctx.needs_input_grad[2]:
+                grad_bias = grad_output.sum([0, 2, 3])
+            return grad_input, grad_weight, grad_bias, grad_scale
+
+    class Conv2dGradWeight(torch.autograd.Function):
+        """dw of the op above.  For a transposed op the roles of (input, grad_output) swap: conv_transpose2d
+        is the adjoint of the conv2d that maps the op's output space to its input space."""
+        @staticmethod
+        def forward(ctx, grad_output, input, in_scale):
+            if not transpose:
+                x_, dy_, sc = input, grad_output, _scale_arg(in_scale, input)
+                d = _make_desc(x_, dy_, False, ci, co, kh, kw, s, padding, groups, flip, sc)
+            else:
+                if in_scale is not None:
+                    raise NotImplementedError('in_scale with conv_transpose2d weight gradients: scale the input explicitly')
+                x_, dy_ = grad_output, input
+                d = _make_desc(x_, dy_, False, co, ci, kh, kw, s, padding, groups, flip)
+            dw = torch.empty(weight_shape, dtype=_lib.acc_dtype(input.dtype), device=input.device)
+            with torch.cuda.device(input.device):
+                rc = _lib.lib().sgb_conv2d_wgrad(d, _lib.ptr(x_), _lib.ptr(dy_), _lib.ptr(dw), _lib.stream_ptr(input.device))
+            _lib.check(rc, 'conv2d_wgrad')
+            ctx.save_for_backward(grad_output, input, in_scale)
+            return dw.to(input.dtype)
+
+        @staticmethod
+        def backward(ctx, grad2_grad_weight):
+            grad_output, input, in_scale = ctx.saved_tensors
+            grad2_grad_output = grad2_input = grad2_scale = None
+            ddw = grad2_grad_weight.to(input.dtype)
+            if ctx.needs_input_grad[0]:
+                grad2_grad_output = Conv2d.apply(input, ddw, None, in_scale)
+                assert grad2_grad_output.shape == grad_output.shape
+            need_x = ctx.needs_input_grad[1]
+            need_s = in_scale is not None and ctx.needs_input_grad[2]
+            if need_x or need_s:
+                p = calc_output_padding(input.shape, grad_output.shape)
+                dgrad = _conv2d_op(transpose=(not transpose), weight_shape=weight_shape, stride=stride, padding=padding,
+                                   output_padding=p, dilation=dilation, groups=groups, flip=flip)
+                g = dgrad.apply(grad_output, ddw, None, None)
+                assert g.shape == input.shape
+                if in_scale is None:
+                    grad2_input = g
+                else:
+                    from . import fma as _fma
+                    if need_x:
+                        grad2_input = _fma.scale_nc(g, in_scale)
+                    if need_s:
+                        grad2_scale = _fma.mul_sum_hw(g, input).to(in_scale.dtype)
+            return grad2_grad_output, grad2_input, grad2_scale
+
+    _cache[key] = Conv2d
+    return Conv2d
