@@ -22,7 +22,10 @@ template <class T, int ACT, int G, int UNROLL>
 __global__ void __launch_bounds__(256) bias_act_vec_kernel(BiasActParams p) {
   typedef typename Acc<T>::type A;
   constexpr int VEC = Vec16<T>::N;
-  const A alpha = A(p.alpha), gain = A(p.gain), clamp = A(p.clamp);
+  // derivative kernels mask on the STORED y: a saturated output was rounded to T, so compare against the
+  // clamp value rounded the same way (fp16(181.02) = 181.0 would otherwise never look saturated)
+  const A alpha = A(p.alpha), gain = A(p.gain);
+  const A clamp = (G > 0 && p.clamp >= 0.f) ? A(to_acc<T>(from_acc<T>(A(p.clamp)))) : A(p.clamp);
   const int64_t nvec = p.size_x / VEC;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   int64_t vi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -99,7 +102,10 @@ __global__ void __launch_bounds__(256) bias_act_vec_kernel(BiasActParams p) {
 template <class T, int ACT, int G>
 __global__ void __launch_bounds__(256) bias_act_scalar_kernel(BiasActParams p, int64_t begin) {
   typedef typename Acc<T>::type A;
-  const A alpha = A(p.alpha), gain = A(p.gain), clamp = A(p.clamp);
+  // derivative kernels mask on the STORED y: a saturated output was rounded to T, so compare against the
+  // clamp value rounded the same way (fp16(181.02) = 181.0 would otherwise never look saturated)
+  const A alpha = A(p.alpha), gain = A(p.gain);
+  const A clamp = (G > 0 && p.clamp >= 0.f) ? A(to_acc<T>(from_acc<T>(A(p.clamp)))) : A(p.clamp);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.size_x; i += stride) {
     A x = to_acc<T>(((const T*)p.x)[i]);

@@ -120,3 +120,56 @@ def is_channels_last(t):
 
 def out_format(t):
     return torch.channels_last if is_channels_last(t) else torch.contiguous_format
+
+
+# ---- optional per-launch timing (bench.py's roofline leg): CUDA events on the launching stream ----------
+class _Profile:
+    def __init__(self):
+        self.records = []          # (kind, start_event, end_event, flops, bytes)
+
+    def summary(self):
+        """kind -> dict(launches, ms, flops, bytes); call after torch.cuda.synchronize()."""
+        out = {}
+        for kind, e0, e1, fl, by in self.records:
+            d = out.setdefault(kind, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+            d['launches'] += 1
+            d['ms'] += e0.elapsed_time(e1)
+            d['flops'] += fl
+            d['bytes'] += by
+        return out
+
+
+PROFILE = None
+
+
+def profile_start():
+    global PROFILE
+    PROFILE = _Profile()
+    return PROFILE
+
+
+def profile_stop():
+    global PROFILE
+    p, PROFILE = PROFILE, None
+    return p
+
+
+class prof:
+    """`with prof(kind, flops, bytes):` around ONE kernel launch; free when profiling is off."""
+    __slots__ = ('kind', 'flops', 'bytes', 'e0')
+
+    def __init__(self, kind, flops=0.0, nbytes=0.0):
+        self.kind, self.flops, self.bytes = kind, flops, nbytes
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.records.append((self.kind, self.e0, e1, float(self.flops), float(self.bytes)))
+        return False

@@ -46,7 +46,8 @@ def _launch(x, b, xref, yref, dy, grad, dim, spec, alpha, gain, clamp):
         return y
     step_b = x.stride(dim) if b is not None else 1
     size_b = b.numel() if b is not None else 1
-    with torch.cuda.device(x.device):
+    nb = x.numel() * x.element_size() * (2 + (xref is not None) + (yref is not None) + (dy is not None))
+    with torch.cuda.device(x.device), _lib.prof('bias_act_g%d' % grad, 0.0, nb):
         rc = _lib.lib().sgb_bias_act(_lib.ptr(x), _lib.ptr(b), _lib.ptr(xref), _lib.ptr(yref), _lib.ptr(dy), _lib.ptr(y),
                                      _lib.dtype_code(x), grad, spec.cuda_idx, alpha, gain, clamp,
                                      x.numel(), size_b, step_b, _lib.stream_ptr(x.device))
@@ -62,7 +63,7 @@ def _sum_to_bias(dx, dim):
         return out.to(dx.dtype)
     inner = dx.stride(dim)
     outer = dx.numel() // (c * inner) if dx.numel() else 0
-    with torch.cuda.device(dx.device):
+    with torch.cuda.device(dx.device), _lib.prof('sum_to_channel', 0.0, dx.numel() * dx.element_size()):
         rc = _lib.lib().sgb_sum_to_channel(_lib.ptr(dx), _lib.ptr(out), _lib.dtype_code(dx), outer, c, inner,
                                            _lib.stream_ptr(dx.device))
     _lib.check(rc, 'sum_to_channel')

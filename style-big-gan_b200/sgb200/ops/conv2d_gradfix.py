@@ -136,7 +136,12 @@ def _conv2d_op(transpose, weight_shape, stride, padding, output_padding, dilatio
             b = bias.contiguous() if bias is not None else None
             if y.numel() > 0:
                 d = _make_desc(input, y, transpose, ci, co, kh, kw, s, padding, groups, flip, sc, b)
-                with torch.cuda.device(input.device):
+                # algorithmic work: non-zero MACs only for the transposed form
+                px = (input.shape[2] * input.shape[3]) if transpose else (oh * ow)
+                flops = 2.0 * input.shape[0] * px * (co // groups) * ci * kh * kw
+                nbytes = (input.numel() + y.numel() + w.numel()) * input.element_size()
+                tc = _lib.lib().sgb_conv2d_uses_tensor_cores(d)
+                with torch.cuda.device(input.device), _lib.prof('conv_fwd_tc' if tc else 'conv_fwd_simt', flops, nbytes):
                     rc = _lib.lib().sgb_conv2d_forward(d, _lib.ptr(input), _lib.ptr(w), _lib.ptr(y), _lib.stream_ptr(input.device))
                 _lib.check(rc, 'conv2d_forward')
             ctx.save_for_backward(input, weight, in_scale)
@@ -184,7 +189,9 @@ def _conv2d_op(transpose, weight_shape, stride, padding, output_padding, dilatio
                 x_, dy_ = grad_output, input
                 d = _make_desc(x_, dy_, False, co, ci, kh, kw, s, padding, groups, flip)
             dw = torch.empty(weight_shape, dtype=_lib.acc_dtype(input.dtype), device=input.device)
-            with torch.cuda.device(input.device):
+            flops = 2.0 * dy_.shape[0] * dy_.shape[2] * dy_.shape[3] * dy_.shape[1] * (x_.shape[1] // groups) * kh * kw
+            nbytes = (x_.numel() + dy_.numel()) * x_.element_size() + dw.numel() * dw.element_size()
+            with torch.cuda.device(input.device), _lib.prof('conv_wgrad', flops, nbytes):
                 rc = _lib.lib().sgb_conv2d_wgrad(d, _lib.ptr(x_), _lib.ptr(dy_), _lib.ptr(dw), _lib.stream_ptr(input.device))
             _lib.check(rc, 'conv2d_wgrad')
             ctx.save_for_backward(grad_output, input, in_scale)

@@ -20,7 +20,7 @@ def _raw_scale(x, s, t):
     s = s.detach().reshape(n, c).to(acc).contiguous()
     if t is not None:
         t = t.detach().reshape(n, h, w).to(acc).contiguous()
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _lib.prof('scale_nc', 0.0, 2 * x.numel() * x.element_size()):
         rc = _lib.lib().sgb_scale_nc(_lib.ptr(x), _lib.ptr(s), _lib.ptr(t), _lib.ptr(y), _lib.dtype_code(x), n, c, h, w,
                                      _lib.strides4(x), _lib.strides4(y), _lib.stream_ptr(x.device))
     _lib.check(rc, 'scale_nc')
@@ -32,7 +32,7 @@ def _raw_mul_sum_hw(a, b):
     out = torch.empty([n, c], dtype=_lib.acc_dtype(a.dtype), device=a.device)
     if out.numel() == 0:
         return out
-    with torch.cuda.device(a.device):
+    with torch.cuda.device(a.device), _lib.prof('mul_sum_hw', 0.0, 2 * a.numel() * a.element_size()):
         rc = _lib.lib().sgb_mul_sum_hw(_lib.ptr(a), _lib.ptr(b), _lib.ptr(out), _lib.dtype_code(a), n, c, h, w,
                                        _lib.strides4(a), _lib.strides4(b), _lib.stream_ptr(a.device))
     _lib.check(rc, 'mul_sum_hw')
@@ -44,7 +44,7 @@ def _raw_sum_c(a):
     out = torch.empty([n, 1, h, w], dtype=_lib.acc_dtype(a.dtype), device=a.device)
     if out.numel() == 0:
         return out
-    with torch.cuda.device(a.device):
+    with torch.cuda.device(a.device), _lib.prof('sum_c', 0.0, a.numel() * a.element_size()):
         rc = _lib.lib().sgb_sum_c(_lib.ptr(a), _lib.ptr(out), _lib.dtype_code(a), n, c, h, w, _lib.strides4(a),
                                   _lib.stream_ptr(a.device))
     _lib.check(rc, 'sum_c')

@@ -80,7 +80,7 @@ def _run(x, f2d, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain)
     y = torch.empty([n, c, oh, ow], dtype=x.dtype, device=x.device, memory_format=_lib.out_format(x))
     if y.numel() == 0:
         return y
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _lib.prof('upfirdn2d', 0.0, (x.numel() + y.numel()) * x.element_size()):
         rc = _lib.lib().sgb_upfirdn2d(_lib.ptr(x), _lib.ptr(f2d), _lib.ptr(y), _lib.dtype_code(x),
                                       n, c, ih, iw, _lib.strides4(x), oh, ow, _lib.strides4(y),
                                       fh, fw, f2d.stride(0), f2d.stride(1),

@@ -1,0 +1,253 @@
+"""Training-step harness for the StyleGAN2 G / D pair on the sgb200 ops (synthetic data; used by bench.py,
+smoke() and the tests).  It reproduces what the reference trainer does per iteration, nothing else:
+
+  phases and lazy regularisation      train_parts/trainers.py:601-633  (Gmain, Greg every g_reg_interval,
+                                       Dmain, Dreg every d_reg_interval; lr and betas rescaled by
+                                       interval / (interval + 1))
+  per-phase work                      train_parts/losses_base.py:43-109 (SG2Loss.run_G with style mixing :131-141)
+  path-length regulariser             train_parts/regularizations.py:11-37
+  R1 regulariser                      train_parts/regularizations.py:40-56
+  non-saturating logistic loss        train_parts/losses.py:47-58 ('softplus')
+  update                              train_parts/trainers.py:745-748 (nan_to_num on grads, Adam step)
+  G_ema                               train_parts/trainers.py:752-761
+
+Data parallelism: one process per GPU; every rank holds full replicas and processes `batch_gpu` images per
+phase; parameter gradients are averaged with ONE flat all-reduce per phase (NCCL over NVLink), which is what
+the reference's DistributedDataParallel wrapping amounts to (trainers.py:883-893) -- the hot path itself has no
+collective.  Logging, snapshots, metrics, augmentation and datasets are out of scope.
+"""
+import copy
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import networks
+from .ops import conv2d_gradfix
+
+
+@dataclass
+class TrainConfig:
+    img_resolution: int = 256
+    img_channels: int = 3
+    z_dim: int = 512
+    w_dim: int = 512
+    channel_base: int = 16384
+    channel_max: int = 512
+    map_layers: int = 6
+    num_fp16_res: int = 0
+    conv_clamp: float = None
+    d_arch: str = 'resnet'
+    mbstd_group_size: int = 8
+    batch_gpu: int = 32
+    lr: float = 0.0025
+    betas: tuple = (0.0, 0.99)
+    g_reg_interval: int = 16
+    d_reg_interval: int = 4
+    r1_gamma: float = 1.0
+    pl_weight: float = 2.0
+    pl_batch_shrink: int = 2
+    pl_decay: float = 0.01
+    style_mixing_prob: float = 0.9
+    use_ppl: bool = True
+    use_r1: bool = True
+    ema_kimg: float = 20.0
+    use_ema: bool = True
+    channels_last: bool = True
+    noise_mode: str = 'random'
+    seed: int = 0
+
+
+# named workloads of BASELINE.json `configs`
+def config_ffhq256(**over):
+    """configs/ffhq_sg2.yaml: 256x256, batch 32/GPU, channel_base 16384, 6 mapping layers, R1 gamma 1 + PPL."""
+    return TrainConfig(**over)
+
+
+def config_f1024(**over):
+    """stylegan2ada/train.py:156,181-182 'stylegan2' preset (config-f): 1024x1024, 4/GPU, fp16 top-4, clamp 256."""
+    kw = dict(img_resolution=1024, channel_base=32768, map_layers=8, num_fp16_res=4, conv_clamp=256.0, batch_gpu=4,
+              mbstd_group_size=4, r1_gamma=10.0, ema_kimg=10.0)
+    kw.update(over)
+    return TrainConfig(**kw)
+
+
+def config_sg2ada64(**over):
+    """configs/sg2ada.yaml at 64x64 batch 8: 2 mapping layers, D 'orig', mbstd 32, R1 gamma 0.01, no PPL, no style mixing."""
+    kw = dict(img_resolution=64, channel_base=32768, map_layers=2, d_arch='orig', mbstd_group_size=32, batch_gpu=8,
+              r1_gamma=0.01, use_ppl=False, style_mixing_prob=0.0, ema_kimg=500.0)
+    kw.update(over)
+    return TrainConfig(**kw)
+
+
+def build_networks(cfg, device):
+    G = networks.Generator(
+        z_dim=cfg.z_dim, c_dim=0, w_dim=cfg.w_dim, img_resolution=cfg.img_resolution, img_channels=cfg.img_channels,
+        mapping_kwargs=dict(num_layers=cfg.map_layers),
+        synthesis_kwargs=dict(channel_base=cfg.channel_base, channel_max=cfg.channel_max, num_fp16_res=cfg.num_fp16_res,
+                              conv_clamp=cfg.conv_clamp, channels_last=cfg.channels_last))
+    D = networks.Discriminator(
+        c_dim=0, img_resolution=cfg.img_resolution, img_channels=cfg.img_channels, architecture=cfg.d_arch,
+        channel_base=cfg.channel_base, channel_max=cfg.channel_max, num_fp16_res=cfg.num_fp16_res, conv_clamp=cfg.conv_clamp,
+        block_kwargs=dict(channels_last=cfg.channels_last), epilogue_kwargs=dict(mbstd_group_size=cfg.mbstd_group_size))
+    return G.to(device), D.to(device)
+
+
+class FlatGradAllReduce:
+    """Average the gradients of a parameter list across ranks with a single flat all-reduce."""
+
+    def __init__(self, params, group=None):
+        self.params = [p for p in params]
+        self.group = group
+
+    def __call__(self):
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+            return 0
+        ps = [p for p in self.params if p.grad is not None]
+        if not ps:
+            return 0
+        flat = torch.cat([p.grad.reshape(-1).to(torch.float32) for p in ps])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        flat.div_(dist.get_world_size(self.group))
+        off = 0
+        for p in ps:
+            n = p.grad.numel()
+            p.grad.copy_(flat[off:off + n].reshape(p.grad.shape))
+            off += n
+        return flat.numel()
+
+
+class Trainer:
+    """One rank's replica: networks, optimisers, phases.  `iteration(real_u8)` is one reference training
+    iteration (all phases due at this batch index) and returns a dict of scalar losses (device tensors)."""
+
+    def __init__(self, cfg, device, rank=0, world_size=1):
+        self.cfg, self.device, self.rank, self.world_size = cfg, torch.device(device), rank, world_size
+        torch.manual_seed(cfg.seed * world_size + rank)       # trainers.py:507-508
+        self.G, self.D = build_networks(cfg, self.device)
+        if world_size > 1:      # same initial weights on every rank (DDP broadcasts them at construction)
+            for p in list(self.G.parameters()) + list(self.D.parameters()):
+                dist.broadcast(p.data, src=0)
+        self.G_ema = copy.deepcopy(self.G).eval().requires_grad_(False) if cfg.use_ema else None
+        self.G.train().requires_grad_(False)
+        self.D.train().requires_grad_(False)
+        self.pl_mean = torch.zeros([], device=self.device)
+        self.batch_idx = 0
+        self.phases = []
+        for name, module, interval, has_reg in [('G', self.G, cfg.g_reg_interval, cfg.use_ppl),
+                                                ('D', self.D, cfg.d_reg_interval, cfg.use_r1)]:
+            params = list(module.parameters())
+            if not has_reg:
+                opt = torch.optim.Adam(params, lr=cfg.lr, betas=tuple(cfg.betas), eps=1e-8, fused=True)
+                self.phases.append(dict(name=name + 'main', module=module, opt=opt, interval=1))
+            else:
+                r = interval / (interval + 1)
+                opt = torch.optim.Adam(params, lr=cfg.lr * r, betas=tuple(b ** r for b in cfg.betas), eps=1e-8, fused=True)
+                self.phases.append(dict(name=name + 'main', module=module, opt=opt, interval=1))
+                self.phases.append(dict(name=name + 'reg', module=module, opt=opt, interval=interval))
+        for ph in self.phases:
+            ph['sync'] = FlatGradAllReduce(ph['module'].parameters())
+
+    # ---- forward helpers (losses_base.py:131-156)
+    def run_G(self, z, return_ws=False):
+        ws = self.G.mapping(z, None)
+        if self.cfg.style_mixing_prob > 0:
+            cutoff = torch.empty([], dtype=torch.int64, device=ws.device).random_(1, ws.shape[1])
+            cutoff = torch.where(torch.rand([], device=ws.device) < self.cfg.style_mixing_prob, cutoff,
+                                 torch.full_like(cutoff, ws.shape[1]))
+            ws2 = self.G.mapping(torch.randn_like(z), None, skip_w_avg_update=True)
+            # ws[:, cutoff:] = ws2[:, cutoff:] without a host sync on `cutoff`
+            idx = torch.arange(ws.shape[1], device=ws.device).reshape(1, -1, 1)
+            ws = torch.where(idx >= cutoff, ws2, ws)
+        img = self.G.synthesis(ws, noise_mode=self.cfg.noise_mode)
+        return (img, ws) if return_ws else img
+
+    def run_D(self, img):
+        return self.D(img, None)
+
+    # ---- phases; each leaves gradients in .grad of the phase's module
+    def phase_Gmain(self, z, gain):
+        logits = self.run_D(self.run_G(z))
+        loss = torch.nn.functional.softplus(-logits).mean()
+        loss.mul(gain).backward()
+        return loss.detach()
+
+    def phase_Greg(self, z, gain, pl_noise=None):
+        cfg = self.cfg
+        n = z.shape[0] // cfg.pl_batch_shrink
+        img, ws = self.run_G(z[:n], return_ws=True)
+        if pl_noise is None:
+            pl_noise = torch.randn_like(img)
+        pl_noise = pl_noise / np.sqrt(img.shape[2] * img.shape[3])
+        with conv2d_gradfix.no_weight_gradients():
+            pl_grads, = torch.autograd.grad(outputs=[(img * pl_noise).sum()], inputs=[ws], create_graph=True, only_inputs=True)
+        pl_lengths = pl_grads.square().sum(2).mean(1).sqrt()
+        pl_mean = self.pl_mean.lerp(pl_lengths.mean(), cfg.pl_decay)
+        self.pl_mean.copy_(pl_mean.detach())
+        loss = (pl_lengths - pl_mean).square() * cfg.pl_weight
+        (img[:, 0, 0, 0] * 0 + loss).mean().mul(gain).backward()
+        return loss.detach().mean()
+
+    def phase_Dmain(self, z, real, gain):
+        with torch.no_grad():
+            fake = self.run_G(z)
+        gen_logits = self.run_D(fake)
+        real_logits = self.run_D(real.detach().requires_grad_(self.cfg.use_r1))   # losses_base.py:72
+        loss = torch.nn.functional.softplus(-real_logits).mean() + torch.nn.functional.softplus(gen_logits).mean()
+        loss.mul(gain).backward()
+        return loss.detach()
+
+    def phase_Dreg(self, real, gain):
+        real = real.detach().requires_grad_(True)
+        real_logits = self.run_D(real)
+        with conv2d_gradfix.no_weight_gradients():
+            r1_grads, = torch.autograd.grad(outputs=[real_logits.sum()], inputs=[real], create_graph=True, only_inputs=True)
+        pen = r1_grads.square().sum([1, 2, 3])
+        loss = pen * (self.cfg.r1_gamma / 2)
+        (real_logits * 0 + loss.unsqueeze(1)).mean().mul(gain).backward()
+        return loss.detach().mean()
+
+    def run_phase(self, ph, real, z):
+        opt, module = ph['opt'], ph['module']
+        opt.zero_grad(set_to_none=True)
+        module.requires_grad_(True)
+        gain = ph['interval']
+        name = ph['name']
+        if name == 'Gmain':
+            val = self.phase_Gmain(z, gain)
+        elif name == 'Greg':
+            val = self.phase_Greg(z, gain)
+        elif name == 'Dmain':
+            val = self.phase_Dmain(z, real, gain)
+        else:
+            val = self.phase_Dreg(real, gain)
+        module.requires_grad_(False)
+        ph['sync']()
+        for p in module.parameters():
+            if p.grad is not None:
+                torch.nan_to_num(p.grad, nan=0, posinf=1e5, neginf=-1e5, out=p.grad)
+        opt.step()
+        return val
+
+    def iteration(self, real_u8, force_all_phases=False):
+        """real_u8: uint8 [batch_gpu, C, R, R] already on the device."""
+        cfg = self.cfg
+        real = real_u8.to(torch.float32) / 127.5 - 1            # trainers.py:716
+        out = {}
+        zs = torch.randn([len(self.phases), cfg.batch_gpu, cfg.z_dim], device=self.device)
+        for ph, z in zip(self.phases, zs):
+            if not force_all_phases and self.batch_idx % ph['interval'] != 0:
+                continue
+            out[ph['name']] = self.run_phase(ph, real, z)
+        if self.G_ema is not None:
+            ema_nimg = cfg.ema_kimg * 1000
+            beta = 0.5 ** (cfg.batch_gpu * self.world_size / max(ema_nimg, 1e-8))
+            with torch.no_grad():
+                ps = list(self.G.parameters())
+                pe = list(self.G_ema.parameters())
+                torch._foreach_lerp_(pe, ps, 1 - beta)           # p_ema = p.lerp(p_ema, beta)
+                for b_ema, b in zip(self.G_ema.buffers(), self.G.buffers()):
+                    b_ema.copy_(b)
+        self.batch_idx += 1
+        return out
