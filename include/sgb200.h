@@ -87,7 +87,17 @@ typedef struct {
   const void*  bias;      /* [co] dtype of x; with act/gain/clamp below = a fused bias_act (grad 0) */
   int32_t act;            /* 0 = no fused bias_act, else SGB_ACT_* */
   float alpha, gain, clamp;
+  /* math mode and scratch */
+  int32_t strict_fp32;    /* SGB_F32 only: 1 = fp32 FFMA arithmetic (1e-4 class); 0 = TF32 tensor cores allowed
+                             (what torch.backends.cudnn.allow_tf32 means for the reference's cuDNN convs) */
+  int32_t reserved0;
+  void*   workspace;      /* caller-owned scratch of >= sgb_conv2d_workspace_bytes(d) bytes, 16-byte aligned, or
+                             NULL (then only the SIMT kernels are used).  Holds the re-packed weights. */
+  int64_t workspace_bytes;
 } sgb_conv_desc;
+
+/* scratch bytes the tensor-core path needs for this descriptor (0 = it cannot be used) */
+int64_t sgb_conv2d_workspace_bytes(const sgb_conv_desc* d);
 
 int sgb_conv2d_forward(const sgb_conv_desc* d, const void* x, const void* w, void* y, void* stream);
 

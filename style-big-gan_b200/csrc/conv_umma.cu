@@ -1,9 +1,442 @@
-// tcgen05 implicit-GEMM convolution (placeholder until the kernel lands: nothing is eligible yet).
+// tcgen05 implicit-GEMM convolution for sm_100a (channels_last activations).
+//
+//   D[m, o] = sum_{tap, c} A[m, (tap, c)] * W[o, (tap, c)]      m = output pixel (n, oy, ox), 128 per CTA
+//
+// Warp roles in a 192-thread CTA (one CTA per 128-pixel x BN-channel output tile):
+//   warps 0-3  producers: thread r owns row r of the A tile.  For every K block (one filter tap x BK channels,
+//              128 bytes) it gathers its pixel's channel vector from global memory with 8 LDG.128 (zero when the
+//              tap falls into padding), optionally multiplies by the per-sample style in_scale[n, c] and rounds
+//              to the MMA operand type, and writes it to shared memory in the canonical K-major UMMA layout
+//              (8-row x 16-byte core matrices, no swizzle: chunk j of row r sits at j*2048 + r*16).  Afterwards the
+//              same four warps run the epilogue: tcgen05.ld of their 32 TMEM lanes, demodulation scale, noise,
+//              bias + activation + clamp, 128-bit stores.
+//   warp 4     MMA issuer: one elected lane issues tcgen05.mma.cta_group::1 (M=128, N=BN, K=32 bytes) from
+//              shared-memory descriptors into a TMEM accumulator, tcgen05.commit releases the stage.
+//   warp 5     weight loader: the weights were re-packed (pack kernel below: flip, transpose, type conversion,
+//              zero padding) into the exact shared-memory image of each B tile, so one cp.async.bulk (TMA bulk
+//              copy, complete_tx on the stage's mbarrier) per K block brings BN x 128 bytes.
+// Synchronisation: full[s] (128 producer arrivals + 1 expect_tx arrival), empty[s] (tcgen05.commit),
+// accum (tcgen05.commit after the last K block).
+//
+// Supported: f16 / bf16 (kind::f16) and f32 storage with TF32 math (kind::tf32), fp32 accumulation; conv2d and
+// conv_transpose2d, any kernel size / stride / padding, groups == 1.
 #include "common.cuh"
+#include "act.cuh"
+
 namespace sgb {
-bool conv_umma_eligible(const sgb_conv_desc*) { return false; }
-int conv_forward_umma(const sgb_conv_desc*, const void*, const void*, void*, cudaStream_t) {
-  set_error("conv_forward_umma: not built");
-  return 1;
+
+constexpr int UM = 128;          // pixels per CTA tile (UMMA M)
+constexpr int KB_BYTES = 128;    // bytes of K per block per row (8 chunks of 16 B)
+constexpr int A_STAGE_BYTES = UM * KB_BYTES;   // 16 KB
+constexpr int NUM_PRODUCERS = 128;
+
+struct UmmaParams {
+  sgb_conv_desc d;
+  const void* x; const void* wpack; void* y;
+  int64_t M;            // n * out_h * out_w
+  int ohw, taps, cblocks, ntiles;
+  int tc;               // elements per 16-byte chunk
+  int vec_store;        // co allows 16-byte stores
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(addr), "r"(cols) : "memory");
+}
+
+template <int KIND>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (KIND == 2) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  }
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+               : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, no-swizzle shared-memory matrix descriptor: core matrices of 8 rows x 16 bytes (128 contiguous bytes);
+// SBO = distance between 8-row groups, LBO = distance between the 16-byte K chunks.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;            // descriptor version (sm_100)
+  return d;                           // base_offset = 0, lbo_mode = 0, layout_type = 0 (no swizzle)
+}
+
+// instruction descriptor: fp32 accumulate, A/B format, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int kind, int n) {
+  return (1u << 4) | ((uint32_t)kind << 7) | ((uint32_t)kind << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t f32_to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+
+// ---- weight re-pack ------------------------------------------------------------------------------------
+// out image per (ntile, tap, cblock): [chunk j (8)][row r (BN)][16 bytes]; zero outside (co, ci).
+template <class T, int KIND>
+__global__ void __launch_bounds__(256) pack_weights_kernel(const T* __restrict__ w, void* __restrict__ out, sgb_conv_desc d,
+                                                           int bn, int ntiles, int cblocks, int tc) {
+  const int taps = d.kh * d.kw;
+  const int bk = 8 * tc;
+  const int64_t total = (int64_t)ntiles * taps * cblocks * 8 * bn * tc;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t = i;
+    const int e = (int)(t % tc); t /= tc;
+    const int r = (int)(t % bn); t /= bn;
+    const int j = (int)(t % 8); t /= 8;
+    const int cb = (int)(t % cblocks); t /= cblocks;
+    const int tap = (int)(t % taps);
+    const int nt = (int)(t / taps);
+    const int o = nt * bn + r, c = cb * bk + j * tc + e;
+    float v = 0.f;
+    if (o < d.co && c < d.ci) {
+      int ky = tap / d.kw, kx = tap - ky * d.kw;
+      if (d.flip) { ky = d.kh - 1 - ky; kx = d.kw - 1 - kx; }
+      const int64_t widx = d.transposed ? ((((int64_t)c * d.co + o) * d.kh + ky) * d.kw + kx)
+                                        : ((((int64_t)o * d.ci + c) * d.kh + ky) * d.kw + kx);
+      v = to_acc<T>(w[widx]);
+    }
+    if (KIND == 2) ((uint32_t*)out)[i] = f32_to_tf32(v);
+    else           ((T*)out)[i] = from_acc<T>(v);
+  }
+}
+
+// ---- main kernel ---------------------------------------------------------------------------------------
+template <class T, int KIND, int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1) conv_umma_kernel(UmmaParams p) {
+  constexpr int TC = 16 / sizeof(T);                 // elements per 16-byte chunk
+  constexpr int BK = 8 * TC;                         // channels per K block
+  constexpr int B_STAGE_BYTES = BN * KB_BYTES;
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr uint32_t IDESC = make_idesc(KIND, BN);
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const sgb_conv_desc& d = p.d;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t m0 = (int64_t)blockIdx.x * UM;
+  const int ntile = blockIdx.y;
+  const int num_kblocks = p.taps * p.cblocks;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; s++) { mbar_init(smem_u32(&full_bar[s]), NUM_PRODUCERS + 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+      mbar_init(smem_u32(&accum_bar), 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(&tmem_base_slot), TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp < 4) {
+    // =========================== producers ===========================
+    const int r = threadIdx.x;                       // row of the tile
+    const int64_t m = m0 + r;
+    const bool row_ok = m < p.M;
+    int n = 0, oy = 0, ox = 0;
+    if (row_ok) { n = (int)(m / p.ohw); const int rem = (int)(m - (int64_t)n * p.ohw); oy = rem / d.out_w; ox = rem - oy * d.out_w; }
+    const T* xn = (const T*)p.x + (int64_t)n * d.x_strides[0];
+    const float* sc = d.in_scale ? (const float*)d.in_scale + (int64_t)n * d.ci : nullptr;
+    uint8_t* a_row = smem + r * 16;
+    int kb = 0;
+    for (int tap = 0; tap < p.taps; tap++) {
+      const int ky = tap / d.kw, kx = tap - ky * d.kw;
+      int iy, ix; bool ok = row_ok;
+      if (!d.transposed) {
+        iy = oy * d.stride + ky - d.pad_y; ix = ox * d.stride + kx - d.pad_x;
+        ok = ok && iy >= 0 && iy < d.in_h && ix >= 0 && ix < d.in_w;
+      } else {
+        const int ty = oy + d.pad_y - ky, tx = ox + d.pad_x - kx;
+        ok = ok && ty >= 0 && tx >= 0 && (ty % d.stride == 0) && (tx % d.stride == 0);
+        iy = ty / d.stride; ix = tx / d.stride;
+        ok = ok && iy < d.in_h && ix < d.in_w;
+      }
+      const T* src = xn + (int64_t)iy * d.x_strides[2] + (int64_t)ix * d.x_strides[3];
+      for (int cb = 0; cb < p.cblocks; cb++, kb++) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        const int c0 = cb * BK;
+        // issue the global loads before waiting for the stage: latency overlaps the wait
+        uint4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const int c = c0 + j * TC;
+          v[j] = (ok && c < d.ci) ? __ldg((const uint4*)(src + c)) : make_uint4(0, 0, 0, 0);
+        }
+        if (sc) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const int c = c0 + j * TC;
+            if (ok && c < d.ci) {
+              if (KIND == 2) {
+                const float4 s4 = __ldg((const float4*)(sc + c));
+                float* f = (float*)&v[j];
+                f[0] *= s4.x; f[1] *= s4.y; f[2] *= s4.z; f[3] *= s4.w;
+              } else {
+                const float4 sa = __ldg((const float4*)(sc + c)), sb = __ldg((const float4*)(sc + c + 4));
+                const float sv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+                T* h = (T*)&v[j];
+#pragma unroll
+                for (int e = 0; e < 8; e++) h[e] = from_acc<T>(to_acc<T>(h[e]) * sv[e]);
+              }
+            }
+          }
+        }
+        if (KIND == 2) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            float* f = (float*)&v[j]; uint32_t* u = (uint32_t*)&v[j];
+            u[0] = f32_to_tf32(f[0]); u[1] = f32_to_tf32(f[1]); u[2] = f32_to_tf32(f[2]); u[3] = f32_to_tf32(f[3]);
+          }
+        }
+        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+        uint8_t* dst = a_row + s * STAGE_BYTES;
+#pragma unroll
+        for (int j = 0; j < 8; j++) *(uint4*)(dst + j * (UM * 16)) = v[j];
+        fence_proxy_async();
+        mbar_arrive(smem_u32(&full_bar[s]));
+      }
+    }
+
+    // =========================== epilogue ===========================
+    mbar_wait(smem_u32(&accum_bar), 0);
+    tc_fence_after();
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const float* out_scale = d.out_scale ? (const float*)d.out_scale + (int64_t)n * d.co : nullptr;
+    const float nz = (d.noise && row_ok) ? ((const float*)d.noise)[((int64_t)n * d.out_h + oy) * d.out_w + ox] : 0.f;
+    const float alpha = d.alpha, gain = d.gain, clamp = d.clamp;
+    T* yrow = (T*)p.y + (int64_t)n * d.y_strides[0] + (int64_t)oy * d.y_strides[2] + (int64_t)ox * d.y_strides[3];
+    const int o_base = ntile * BN;
+#pragma unroll 1
+    for (int cc = 0; cc < BN; cc += 16) {
+      uint32_t acc[16];
+      tmem_ld16(lane_addr + cc, acc);          // warp-collective: every lane participates, stores are predicated
+      if (!row_ok) continue;
+      float val[16];
+#pragma unroll
+      for (int e = 0; e < 16; e++) {
+        const int o = o_base + cc + e;
+        float a = __uint_as_float(acc[e]);
+        if (o < d.co) {
+          if (out_scale) a *= out_scale[o];
+          a += nz;
+          if (d.act) {
+            if (d.bias) a += to_acc<T>(((const T*)d.bias)[o]);
+            a = act_forward<float>(d.act, a, alpha, gain, clamp);
+          }
+        }
+        val[e] = a;
+      }
+      if (p.vec_store) {
+#pragma unroll
+        for (int g = 0; g < 16 / TC; g++) {
+          const int o = o_base + cc + g * TC;
+          if (o < d.co) {
+            Vec16<T> pk;
+#pragma unroll
+            for (int e = 0; e < TC; e++) pk.v[e] = from_acc<T>(val[g * TC + e]);
+            *(uint4*)(yrow + o) = pk.raw;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+          const int o = o_base + cc + e;
+          if (o < d.co) yrow[(int64_t)o * d.y_strides[1]] = from_acc<T>(val[e]);
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 4) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kblocks; kb++) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(smem_u32(&full_bar[s]), ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {          // 4 x (2 chunks of 16 bytes) = 128 bytes of K
+          const uint64_t adesc = make_smem_desc(a_addr + kk * 2 * (UM * 16), UM * 16, 128);
+          const uint64_t bdesc = make_smem_desc(b_addr + kk * 2 * (BN * 16), BN * 16, 128);
+          umma<KIND>(tmem_base, adesc, bdesc, IDESC, (kb > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&empty_bar[s]));     // frees the stage once these MMAs have read it
+      }
+      umma_commit(smem_u32(&accum_bar));          // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // =========================== weight loader ===========================
+    if (lane == 0) {
+      const uint8_t* wsrc = (const uint8_t*)p.wpack + (int64_t)ntile * num_kblocks * B_STAGE_BYTES;
+      for (int kb = 0; kb < num_kblocks; kb++) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+        const uint32_t bar = smem_u32(&full_bar[s]);
+        mbar_arrive_expect_tx(bar, B_STAGE_BYTES);
+        bulk_copy_g2s(smem_u32(smem + s * STAGE_BYTES + A_STAGE_BYTES), wsrc + (int64_t)kb * B_STAGE_BYTES, B_STAGE_BYTES, bar);
+      }
+    }
+    __syncwarp();
+  }
+
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------
+static int pick_bn(int co) {
+  if (co <= 16) return 16;
+  if (co <= 32) return 32;
+  if (co <= 64) return 64;
+  if (co <= 128) return 128;
+  return 256;
+}
+static int stages_for(int bn) { return bn == 256 ? 4 : (bn == 128 ? 3 : 4); }
+
+static int elem_size(int dtype) { return dtype == SGB_F32 ? 4 : 2; }
+
+bool conv_umma_eligible(const sgb_conv_desc* d) {
+  if (d->dtype != SGB_F32 && d->dtype != SGB_F16 && d->dtype != SGB_BF16) return false;
+  if (d->dtype == SGB_F32 && d->strict_fp32) return false;
+  if (d->groups != 1) return false;
+  const int tc = 16 / elem_size(d->dtype);
+  if (d->ci % tc != 0) return false;
+  if (d->x_strides[1] != 1 || d->y_strides[1] != 1) return false;              // channels_last only
+  if (d->x_strides[0] % tc || d->x_strides[2] % tc || d->x_strides[3] % tc) return false;
+  if (d->kh * d->kw > 49) return false;
+  if (!d->workspace || d->workspace_bytes < sgb_conv2d_workspace_bytes(d)) return false;
+  return true;
+}
+
+template <class T, int KIND, int BN>
+static int launch_umma(const sgb_conv_desc* d, const void* x, const void* w, void* y, cudaStream_t s) {
+  constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 3 : 4);
+  constexpr int TC = 16 / sizeof(T);
+  UmmaParams p; p.d = *d; p.x = x; p.y = y; p.wpack = d->workspace;
+  p.M = (int64_t)d->n * d->out_h * d->out_w; p.ohw = d->out_h * d->out_w; p.taps = d->kh * d->kw;
+  p.cblocks = (d->ci + 8 * TC - 1) / (8 * TC); p.ntiles = (d->co + BN - 1) / BN; p.tc = TC;
+  const bool y_al = aligned16(y) && d->y_strides[0] % TC == 0 && d->y_strides[2] % TC == 0 && d->y_strides[3] % TC == 0;
+  p.vec_store = (d->co % TC == 0 && y_al) ? 1 : 0;
+  SGB_REQUIRE(aligned16(x) && aligned16(d->workspace), "x and workspace must be 16-byte aligned");
+  // 1) re-pack the weights into B-tile images
+  {
+    const int64_t total = (int64_t)p.ntiles * p.taps * p.cblocks * 8 * BN * TC;
+    int64_t blocks = ceil_div(total, 256); if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    pack_weights_kernel<T, KIND><<<(unsigned)blocks, 256, 0, s>>>((const T*)w, d->workspace, *d, BN, p.ntiles, p.cblocks, TC);
+    SGB_LAUNCH_CHECK();
+  }
+  // 2) implicit GEMM
+  const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + BN * KB_BYTES) + 1024;
+  auto kern = conv_umma_kernel<T, KIND, BN, STAGES>;
+  static bool attr_set = false;          // per template instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    SGB_REQUIRE(e == cudaSuccess, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int64_t gx = ceil_div(p.M, UM);
+  SGB_REQUIRE(gx <= 0x7fffffff && p.ntiles <= 65535, "problem too large for the UMMA conv grid");
+  kern<<<dim3((unsigned)gx, (unsigned)p.ntiles), 192, smem, s>>>(p);
+  SGB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <class T, int KIND>
+static int dispatch_bn(const sgb_conv_desc* d, const void* x, const void* w, void* y, cudaStream_t s) {
+  switch (pick_bn(d->co)) {
+    case 16:  return launch_umma<T, KIND, 16>(d, x, w, y, s);
+    case 32:  return launch_umma<T, KIND, 32>(d, x, w, y, s);
+    case 64:  return launch_umma<T, KIND, 64>(d, x, w, y, s);
+    case 128: return launch_umma<T, KIND, 128>(d, x, w, y, s);
+    default:  return launch_umma<T, KIND, 256>(d, x, w, y, s);
+  }
+}
+
+int conv_forward_umma(const sgb_conv_desc* d, const void* x, const void* w, void* y, cudaStream_t s) {
+  if (d->dtype == SGB_F16) return dispatch_bn<__half, 0>(d, x, w, y, s);
+  if (d->dtype == SGB_BF16) return dispatch_bn<__nv_bfloat16, 1>(d, x, w, y, s);
+  return dispatch_bn<float, 2>(d, x, w, y, s);
+}
+
 }  // namespace sgb
+
+extern "C" int64_t sgb_conv2d_workspace_bytes(const sgb_conv_desc* d) {
+  if (!d || d->groups != 1) return 0;
+  if (d->dtype != SGB_F32 && d->dtype != SGB_F16 && d->dtype != SGB_BF16) return 0;
+  const int es = sgb::elem_size(d->dtype);
+  const int tc = 16 / es;
+  const int bn = sgb::pick_bn(d->co);
+  const int64_t ntiles = (d->co + bn - 1) / bn, cblocks = (d->ci + 8 * tc - 1) / (8 * tc);
+  return ntiles * d->kh * d->kw * cblocks * bn * sgb::KB_BYTES;
+}

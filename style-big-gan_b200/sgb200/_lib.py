@@ -33,6 +33,7 @@ class ConvDesc(_c.Structure):
         ('x_strides', _I64x4), ('y_strides', _I64x4),
         ('in_scale', _vp), ('out_scale', _vp), ('noise', _vp), ('bias', _vp),
         ('act', _c.c_int32), ('alpha', _flt), ('gain', _flt), ('clamp', _flt),
+        ('strict_fp32', _c.c_int32), ('reserved0', _c.c_int32), ('workspace', _vp), ('workspace_bytes', _i64),
     ]
 
 
@@ -48,6 +49,7 @@ SIGNATURES = {
     'sgb_conv2d_forward': (_int, [_c.POINTER(ConvDesc), _vp, _vp, _vp, _vp]),
     'sgb_conv2d_wgrad': (_int, [_c.POINTER(ConvDesc), _vp, _vp, _vp, _vp]),
     'sgb_conv2d_uses_tensor_cores': (_int, [_c.POINTER(ConvDesc)]),
+    'sgb_conv2d_workspace_bytes': (_i64, [_c.POINTER(ConvDesc)]),
     'sgb_scale_nc': (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _c.POINTER(_i64), _c.POINTER(_i64), _vp]),
     'sgb_mul_sum_hw': (_int, [_vp, _vp, _vp, _int, _int, _int, _int, _int, _c.POINTER(_i64), _c.POINTER(_i64), _vp]),
     'sgb_sum_c': (_int, [_vp, _vp, _int, _int, _int, _int, _int, _c.POINTER(_i64), _vp]),

@@ -18,6 +18,7 @@ import torch
 from .. import _lib
 
 enabled = True                      # kept for API compatibility; the custom op is the only implementation
+use_tensor_cores = True             # False routes every convolution to the SIMT kernels (debugging / A-B tests)
 weight_gradients_disabled = False   # forcefully disable computation of gradients with respect to the weights
 
 
@@ -66,7 +67,23 @@ def _make_desc(x, y, transposed, ci, co, kh, kw, stride, pad, groups, flip, in_s
     d.bias = _lib.ptr(bias)
     d.act = 1 if bias is not None else 0       # linear, gain 1, no clamp == plain bias add
     d.alpha, d.gain, d.clamp = 0.0, 1.0, -1.0
+    # fp32 tensors: TF32 tensor cores only if the caller allows it the way it would for cuDNN
+    # (reference trainers.py:511 sets torch.backends.cudnn.allow_tf32 from perf.allow_tf32)
+    d.strict_fp32 = 0 if torch.backends.cudnn.allow_tf32 else 1
+    d.workspace, d.workspace_bytes = None, 0
     return d
+
+
+def _attach_workspace(d, device):
+    """Scratch for the tensor-core path (re-packed weights); returns the tensor so it outlives the launch."""
+    if not use_tensor_cores:
+        return None
+    nbytes = int(_lib.lib().sgb_conv2d_workspace_bytes(d))
+    if nbytes <= 0:
+        return None
+    ws = torch.empty([nbytes], dtype=torch.uint8, device=device)
+    d.workspace, d.workspace_bytes = ws.data_ptr(), nbytes
+    return ws
 
 
 def _scale_arg(in_scale, x):
@@ -140,6 +157,7 @@ def _conv2d_op(transpose, weight_shape, stride, padding, output_padding, dilatio
                 px = (input.shape[2] * input.shape[3]) if transpose else (oh * ow)
                 flops = 2.0 * input.shape[0] * px * (co // groups) * ci * kh * kw
                 nbytes = (input.numel() + y.numel() + w.numel()) * input.element_size()
+                ws = _attach_workspace(d, input.device)
                 tc = _lib.lib().sgb_conv2d_uses_tensor_cores(d)
                 with torch.cuda.device(input.device), _lib.prof('conv_fwd_tc' if tc else 'conv_fwd_simt', flops, nbytes):
                     rc = _lib.lib().sgb_conv2d_forward(d, _lib.ptr(input), _lib.ptr(w), _lib.ptr(y), _lib.stream_ptr(input.device))

@@ -25,3 +25,14 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if 'gpu' in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _strict_fp32_convs():
+    """Parity tests run fp32 convolutions in strict fp32 (the reference default, trainers.py:384,511);
+    TF32 tensor-core tests switch it on explicitly."""
+    import torch
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32 = old

@@ -1,0 +1,116 @@
+"""GPU: the tcgen05 implicit-GEMM convolution (channels_last, f16 / bf16 / TF32) against the CPU oracle, and
+against the SIMT kernel on the same inputs.  Tolerance 1e-2 relative (tensor-core class, BASELINE.json)."""
+import math
+
+import pytest
+import torch
+
+from helpers import assert_close, rel_err
+from oracle import ref_ops as R
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+TOL = 1e-2
+
+
+def _desc_uses_tc(x, w, transposed=False, stride=1, pad=0):
+    from sgb200.ops import conv2d_gradfix as cg
+    from sgb200 import _lib
+    n, ci, h, wd = x.shape
+    if not transposed:
+        co, kh, kw = w.shape[0], w.shape[2], w.shape[3]
+        oh, ow = (h + 2 * pad - kh) // stride + 1, (wd + 2 * pad - kw) // stride + 1
+    else:
+        co, kh, kw = w.shape[1], w.shape[2], w.shape[3]
+        oh, ow = (h - 1) * stride - 2 * pad + kh, (wd - 1) * stride - 2 * pad + kw
+    y = torch.empty([n, co, oh, ow], dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+    d = cg._make_desc(x, y, transposed, ci, co, kh, kw, stride, (pad, pad), 1, False)
+    ws = cg._attach_workspace(d, x.device)
+    return bool(_lib.lib().sgb_conv2d_uses_tensor_cores(d))
+
+
+def _cl(t):
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+def test_probe_1x1_gemm_fp16():
+    """Smallest case: a 1x1 convolution is a plain [pixels x ci] x [ci x co] GEMM -> checks the UMMA descriptors."""
+    from sgb200.ops import conv2d_gradfix as cg
+    torch.manual_seed(0)
+    x = _cl(torch.randn(1, 64, 16, 16).to(DEV, torch.float16))
+    w = (torch.randn(64, 64, 1, 1) / 8).to(DEV, torch.float16)
+    assert _desc_uses_tc(x, w)
+    y = cg.conv2d(x, w)
+    yo = torch.nn.functional.conv2d(x.cpu().float(), w.cpu().float())
+    assert_close(y, yo, TOL, '1x1 fp16')
+
+
+@pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16, torch.float32])
+@pytest.mark.parametrize('case', [
+    # (N, Ci, Co, H, W, k, stride, pad, transposed)
+    (1, 64, 64, 16, 16, 1, 1, 0, False),
+    (2, 64, 64, 16, 16, 3, 1, 1, False),
+    (2, 32, 48, 12, 20, 3, 1, 1, False),      # M tail, co not a power of two
+    (3, 72, 24, 9, 9, 3, 1, 1, False),        # K tail (72 = 64 + 8), several samples per tile
+    (2, 64, 128, 17, 17, 3, 2, 0, False),     # stride 2 (D down path, after the FIR)
+    (2, 128, 64, 8, 8, 3, 1, 1, True),        # transposed stride 1 (dgrad of a 3x3 conv)
+    (2, 64, 32, 8, 8, 3, 2, 0, True),         # transposed stride 2 (G up path)
+    (1, 512, 512, 4, 4, 3, 1, 1, False),      # N tiles > 1, tiny image
+    (2, 64, 3, 16, 16, 1, 1, 0, False),       # toRGB: co = 3
+    (1, 256, 272, 6, 6, 3, 1, 1, False),      # co tail over two N tiles
+])
+def test_umma_conv_vs_oracle(dtype, case):
+    from sgb200.ops import conv2d_gradfix as cg
+    n, ci, co, h, wd, k, stride, pad, tr = case
+    torch.manual_seed(1)
+    torch.backends.cudnn.allow_tf32 = True
+    x = _cl(torch.randn(n, ci, h, wd).to(DEV, dtype))
+    wshape = (ci, co, k, k) if tr else (co, ci, k, k)
+    w = (torch.randn(wshape) / math.sqrt(ci * k * k)).to(DEV, dtype)
+    assert _desc_uses_tc(x, w, tr, stride, pad)
+    op = cg.conv_transpose2d if tr else cg.conv2d
+    y = op(x, w, stride=stride, padding=pad)
+    fo = torch.nn.functional.conv_transpose2d if tr else torch.nn.functional.conv2d
+    yo = fo(x.cpu().float(), w.cpu().float(), stride=stride, padding=pad)
+    assert y.shape == yo.shape and y.is_contiguous(memory_format=torch.channels_last)
+    assert_close(y, yo, TOL, f'{case} {dtype}')
+    # same inputs through the SIMT kernel: the two CUDA paths must agree as well
+    cg.use_tensor_cores = False
+    try:
+        ys = op(x, w, stride=stride, padding=pad)
+    finally:
+        cg.use_tensor_cores = True
+    assert_close(y, ys.float().cpu(), TOL, f'{case} {dtype} vs simt')
+
+
+@pytest.mark.parametrize('dtype', [torch.float16, torch.float32])
+def test_umma_in_scale_and_flip(dtype):
+    from sgb200.ops import conv2d_gradfix as cg
+    torch.manual_seed(2)
+    torch.backends.cudnn.allow_tf32 = True
+    x = _cl(torch.randn(3, 64, 8, 8).to(DEV, dtype))
+    w = (torch.randn(32, 64, 3, 3) / 24).to(DEV, dtype)
+    s = (torch.randn(3, 64) + 1).to(DEV)
+    y = cg.conv2d(x, w, padding=1, flip_weight=True, in_scale=s)
+    yo = torch.nn.functional.conv2d(x.cpu().float() * s.cpu()[:, :, None, None], w.cpu().float().flip([2, 3]), padding=1)
+    assert_close(y, yo, TOL, 'in_scale + flip')
+
+
+def test_umma_gradients_fp16():
+    """dgrad runs through the transposed tensor-core kernel; compare all gradients with the oracle."""
+    from sgb200.ops import conv2d_resample
+    torch.manual_seed(3)
+    f = R.setup_filter([1, 3, 3, 1])
+    for up, down in [(1, 1), (2, 1), (1, 2)]:
+        x = _cl(torch.randn(2, 64, 16, 16).to(DEV, torch.float16)).requires_grad_(True)
+        w = (torch.randn(64, 64, 3, 3) / 24).to(DEV, torch.float16).requires_grad_(True)
+        y = conv2d_resample.conv2d_resample(x, w, f=f.to(DEV), up=up, down=down, padding=1, flip_weight=(up == 1))
+        xo = x.detach().cpu().float().requires_grad_(True)
+        wo = w.detach().cpu().float().requires_grad_(True)
+        yo = R.conv2d_resample(xo, wo, f=f, up=up, down=down, padding=1, flip_weight=(up == 1))
+        assert_close(y, yo, TOL, f'y up{up} down{down}')
+        dy = torch.randn_like(yo)
+        dx, dw = torch.autograd.grad(y, [x, w], dy.to(DEV, torch.float16))
+        dxo, dwo = torch.autograd.grad(yo, [xo, wo], dy)
+        assert_close(dx, dxo, TOL, f'dx up{up} down{down}')
+        assert_close(dw, dwo, TOL, f'dw up{up} down{down}')
