@@ -163,6 +163,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='ffhq256', choices=sorted(WORKLOAD_DESC))
+    ap.add_argument('--fp32-mode', default='tf32', choices=['tf32', 'strict'],
+                    help="arithmetic of fp32 convolutions: 'tf32' = TF32 tensor cores (torch.backends.cudnn.allow_tf32=True, "
+                         "1e-2 class), 'strict' = fp32 FFMA (the reference default perf.allow_tf32=False, 1e-4 class)")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--breakdown', default=None, help='write the per-kernel-family time table (json) here')
@@ -186,6 +189,8 @@ def main():
     _lib.lib()     # fail loudly if the CUDA library is missing
 
     torch.backends.cudnn.benchmark = False
+    torch.backends.cudnn.allow_tf32 = (args.fp32_mode == 'tf32')
+    torch.backends.cuda.matmul.allow_tf32 = (args.fp32_mode == 'tf32')
     cfg = workload_config(args.workload)
     tr = training.Trainer(cfg, device, rank=rank, world_size=world)
     R, N = cfg.img_resolution, cfg.batch_gpu
@@ -277,10 +282,10 @@ def main():
 
     line = dict(metric='train img/s (G+D)', value=value, unit='img/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
-                dtype='f32 storage, tf32/f32 math' if cfg.num_fp16_res == 0 else 'f16 (top res) + f32', data='synthetic',
+                dtype=('tf32' if args.fp32_mode == 'tf32' else 'f32') + ('' if cfg.num_fp16_res == 0 else '+f16'), data='synthetic',
                 config=dict(workload=WORKLOAD_DESC[args.workload], batch_per_gpu=N, global_batch=N * world, resolution=R,
                             parallelism=f'dp{world}', g_reg_interval=cfg.g_reg_interval, d_reg_interval=cfg.d_reg_interval,
-                            layout='channels_last' if cfg.channels_last else 'nchw',
+                            layout='channels_last' if cfg.channels_last else 'nchw', fp32_mode=args.fp32_mode,
                             l2='working set per step (activations, GBs) far exceeds the 126 MB L2; no explicit flush'),
                 gpu_launches=int(launches), e2e=e2e, roofline=roof, cpu_baseline=cpu, clocks=clocks)
     print(json.dumps(line), flush=True)

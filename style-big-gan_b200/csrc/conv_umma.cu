@@ -117,8 +117,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 }
 
 // instruction descriptor: fp32 accumulate, A/B format, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int kind, int n) {
-  return (1u << 4) | ((uint32_t)kind << 7) | ((uint32_t)kind << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int kind, int n, int mn_major = 0) {
+  return (1u << 4) | ((uint32_t)kind << 7) | ((uint32_t)kind << 10) | ((uint32_t)mn_major << 15) | ((uint32_t)mn_major << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
 }
 
 __device__ __forceinline__ uint32_t f32_to_tf32(float v) {
@@ -354,6 +355,185 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(UmmaParams p) {
   }
 }
 
+
+// ---- weight gradient ---------------------------------------------------------------------------------------
+//   dW[o, c, tap] = sum_p dy[p, o] * xs[p_in(p, tap), c]        p = output pixel (n, oy, ox)
+// One CTA owns (128 output channels) x (BNC input channels) x (one filter tap) x (one slice of the pixels = split-K).
+// Both operands are [pixel][channel] in memory with the channel contiguous, i.e. MN-major for a GEMM whose K is the
+// pixel index: the 128 producer threads copy 16-byte channel chunks of PPB pixels per K block into the canonical
+// MN-major UMMA layout ([chunk][pixel][16 B]: SBO = PPB*16 between channel chunks, LBO = 128 between groups of 8 pixels),
+// the x operand gathered at the tap's offset (zero in the padding) and multiplied by in_scale when set.
+// The fp32 accumulator tile is added to dW with red.global.add.f32 (dW zeroed by the launcher).
+struct WgradParams {
+  sgb_conv_desc d;
+  const void* x; const void* dy; float* dw;
+  int64_t P;            // n * out_h * out_w
+  int ohw, taps, ctiles, otiles, splits;
+  int64_t chunk;        // pixels per split (multiple of PPB)
+};
+
+template <class T, int KIND, int BNC, int STAGES>
+__global__ void __launch_bounds__(160, 1) conv_wgrad_umma_kernel(WgradParams p) {
+  constexpr int TC = 16 / sizeof(T);
+  constexpr int PPB = 8 * TC;                        // pixels per K block: 64 (16-bit) / 32 (tf32) -> 4 MMAs
+  constexpr int SPLIT = 128 / PPB;                   // producer thread groups per pixel
+  constexpr int A_CHUNKS = UM / TC;                  // 16-byte chunks per pixel of the dy tile
+  constexpr int B_CHUNKS = BNC / TC;
+  constexpr int A_PER_T = A_CHUNKS / SPLIT, B_PER_T = B_CHUNKS / SPLIT;
+  constexpr int A_BYTES = UM * PPB * (int)sizeof(T); // 16 KB
+  constexpr int B_BYTES = BNC * PPB * (int)sizeof(T);
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = BNC < 32 ? 32 : BNC;
+  constexpr uint32_t IDESC = make_idesc(KIND, BNC, 1);
+  constexpr int K_PER_MMA = 32 / (int)sizeof(T);     // 16 / 8 pixels
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const sgb_conv_desc& d = p.d;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int otile = blockIdx.x;
+  const int tap = blockIdx.y / p.ctiles, ctile = blockIdx.y - tap * p.ctiles;
+  const int split = blockIdx.z;
+  const int64_t p_begin = (int64_t)split * p.chunk;
+  const int64_t p_end = (p_begin + p.chunk < p.P) ? p_begin + p.chunk : p.P;
+  const int num_kblocks = p_end > p_begin ? (int)((p_end - p_begin + PPB - 1) / PPB) : 0;
+  const int ky = tap / d.kw, kx = tap - ky * d.kw;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; s++) { mbar_init(smem_u32(&full_bar[s]), NUM_PRODUCERS); mbar_init(smem_u32(&empty_bar[s]), 1); }
+      mbar_init(smem_u32(&accum_bar), 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(&tmem_base_slot), TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp < 4) {
+    const int t = threadIdx.x;
+    const int pl = t % PPB, grp = t / PPB;            // pixel within the block, channel group
+    const int o_first = otile * UM + grp * (A_PER_T * TC);
+    const int c_first = ctile * BNC + grp * (B_PER_T * TC);
+    for (int kb = 0; kb < num_kblocks; kb++) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      const int64_t pix = p_begin + (int64_t)kb * PPB + pl;
+      const bool pok = pix < p_end;
+      int n = 0, oy = 0, ox = 0;
+      if (pok) { n = (int)(pix / p.ohw); const int rem = (int)(pix - (int64_t)n * p.ohw); oy = rem / d.out_w; ox = rem - oy * d.out_w; }
+      const int iy = oy * d.stride + ky - d.pad_y, ix = ox * d.stride + kx - d.pad_x;
+      const bool xok = pok && iy >= 0 && iy < d.in_h && ix >= 0 && ix < d.in_w;
+      const T* dyp = (const T*)p.dy + (int64_t)n * d.y_strides[0] + (int64_t)oy * d.y_strides[2] + (int64_t)ox * d.y_strides[3];
+      const T* xp = (const T*)p.x + (int64_t)n * d.x_strides[0] + (int64_t)iy * d.x_strides[2] + (int64_t)ix * d.x_strides[3];
+      const float* sc = d.in_scale ? (const float*)d.in_scale + (int64_t)n * d.ci : nullptr;
+      uint4 va[A_PER_T], vb[B_PER_T];
+#pragma unroll
+      for (int j = 0; j < A_PER_T; j++) {
+        const int o = o_first + j * TC;
+        va[j] = (pok && o < d.co) ? __ldg((const uint4*)(dyp + o)) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int j = 0; j < B_PER_T; j++) {
+        const int c = c_first + j * TC;
+        vb[j] = (xok && c < d.ci) ? __ldg((const uint4*)(xp + c)) : make_uint4(0, 0, 0, 0);
+      }
+      if (sc) {
+#pragma unroll
+        for (int j = 0; j < B_PER_T; j++) {
+          const int c = c_first + j * TC;
+          if (xok && c < d.ci) {
+            if (KIND == 2) {
+              const float4 s4 = __ldg((const float4*)(sc + c));
+              float* f = (float*)&vb[j];
+              f[0] *= s4.x; f[1] *= s4.y; f[2] *= s4.z; f[3] *= s4.w;
+            } else {
+              const float4 sa = __ldg((const float4*)(sc + c)), sb = __ldg((const float4*)(sc + c + 4));
+              const float sv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+              T* h = (T*)&vb[j];
+#pragma unroll
+              for (int e = 0; e < 8; e++) h[e] = from_acc<T>(to_acc<T>(h[e]) * sv[e]);
+            }
+          }
+        }
+      }
+      if (KIND == 2) {
+#pragma unroll
+        for (int j = 0; j < A_PER_T; j++) {
+          float* f = (float*)&va[j]; uint32_t* u = (uint32_t*)&va[j];
+          u[0] = f32_to_tf32(f[0]); u[1] = f32_to_tf32(f[1]); u[2] = f32_to_tf32(f[2]); u[3] = f32_to_tf32(f[3]);
+        }
+#pragma unroll
+        for (int j = 0; j < B_PER_T; j++) {
+          float* f = (float*)&vb[j]; uint32_t* u = (uint32_t*)&vb[j];
+          u[0] = f32_to_tf32(f[0]); u[1] = f32_to_tf32(f[1]); u[2] = f32_to_tf32(f[2]); u[3] = f32_to_tf32(f[3]);
+        }
+      }
+      mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+      uint8_t* a_dst = smem + s * STAGE_BYTES + pl * 16;
+      uint8_t* b_dst = a_dst + A_BYTES;
+#pragma unroll
+      for (int j = 0; j < A_PER_T; j++) *(uint4*)(a_dst + (grp * A_PER_T + j) * (PPB * 16)) = va[j];
+#pragma unroll
+      for (int j = 0; j < B_PER_T; j++) *(uint4*)(b_dst + (grp * B_PER_T + j) * (PPB * 16)) = vb[j];
+      fence_proxy_async();
+      mbar_arrive(smem_u32(&full_bar[s]));
+    }
+
+    // epilogue: lane = output channel, columns = input channels of this tile
+    if (num_kblocks > 0) {
+      mbar_wait(smem_u32(&accum_bar), 0);
+      tc_fence_after();
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+      const int o = otile * UM + threadIdx.x;
+      const int wy = d.flip ? d.kh - 1 - ky : ky, wx = d.flip ? d.kw - 1 - kx : kx;
+#pragma unroll 1
+      for (int cc = 0; cc < BNC; cc += 16) {
+        uint32_t acc[16];
+        tmem_ld16(lane_addr + cc, acc);
+        if (o >= d.co) continue;
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+          const int c = ctile * BNC + cc + e;
+          if (c < d.ci) atomicAdd(p.dw + (((int64_t)o * d.ci + c) * d.kh + wy) * d.kw + wx, __uint_as_float(acc[e]));
+        }
+      }
+      tc_fence_before();
+    }
+  } else {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kblocks; kb++) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(smem_u32(&full_bar[s]), ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < PPB / K_PER_MMA; kk++) {
+          const uint64_t adesc = make_smem_desc(a_addr + kk * K_PER_MMA * 16, 128, PPB * 16);
+          const uint64_t bdesc = make_smem_desc(b_addr + kk * K_PER_MMA * 16, 128, PPB * 16);
+          umma<KIND>(tmem_base, adesc, bdesc, IDESC, (kb > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&empty_bar[s]));
+      }
+      if (num_kblocks > 0) umma_commit(smem_u32(&accum_bar));
+    }
+    __syncwarp();
+  }
+
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
 // ---- host side -------------------------------------------------------------------------------------------
 static int pick_bn(int co) {
   if (co <= 16) return 16;
@@ -369,6 +549,7 @@ static int elem_size(int dtype) { return dtype == SGB_F32 ? 4 : 2; }
 bool conv_umma_eligible(const sgb_conv_desc* d) {
   if (d->dtype != SGB_F32 && d->dtype != SGB_F16 && d->dtype != SGB_BF16) return false;
   if (d->dtype == SGB_F32 && d->strict_fp32) return false;
+  if (d->force_simt) return false;
   if (d->groups != 1) return false;
   const int tc = 16 / elem_size(d->dtype);
   if (d->ci % tc != 0) return false;
@@ -427,6 +608,71 @@ int conv_forward_umma(const sgb_conv_desc* d, const void* x, const void* w, void
   if (d->dtype == SGB_F16) return dispatch_bn<__half, 0>(d, x, w, y, s);
   if (d->dtype == SGB_BF16) return dispatch_bn<__nv_bfloat16, 1>(d, x, w, y, s);
   return dispatch_bn<float, 2>(d, x, w, y, s);
+}
+
+
+bool conv_wgrad_umma_eligible(const sgb_conv_desc* d) {
+  if (d->dtype != SGB_F32 && d->dtype != SGB_F16 && d->dtype != SGB_BF16) return false;
+  if (d->dtype == SGB_F32 && d->strict_fp32) return false;
+  if (d->force_simt) return false;
+  if (d->groups != 1 || d->transposed) return false;
+  const int tc = 16 / elem_size(d->dtype);
+  if (d->ci % tc != 0 || d->co % tc != 0) return false;
+  if (d->x_strides[1] != 1 || d->y_strides[1] != 1) return false;
+  if (d->x_strides[0] % tc || d->x_strides[2] % tc || d->x_strides[3] % tc) return false;
+  if (d->y_strides[0] % tc || d->y_strides[2] % tc || d->y_strides[3] % tc) return false;
+  if (d->kh * d->kw > 49) return false;
+  return true;
+}
+
+template <class T, int KIND, int BNC>
+static int launch_wgrad_umma(const sgb_conv_desc* d, const void* x, const void* dy, float* dw, cudaStream_t s) {
+  constexpr int STAGES = BNC == 256 ? 4 : (BNC == 128 ? 3 : 4);
+  constexpr int TC = 16 / sizeof(T);
+  constexpr int PPB = 8 * TC;
+  WgradParams p; p.d = *d; p.x = x; p.dy = dy; p.dw = dw;
+  p.P = (int64_t)d->n * d->out_h * d->out_w; p.ohw = d->out_h * d->out_w; p.taps = d->kh * d->kw;
+  p.ctiles = (d->ci + BNC - 1) / BNC; p.otiles = (d->co + UM - 1) / UM;
+  SGB_REQUIRE(aligned16(x) && aligned16(dy), "x and dy must be 16-byte aligned");
+  const int64_t tiles = (int64_t)p.otiles * p.ctiles * p.taps;
+  int64_t splits = ceil_div((int64_t)kNumSMs * 2, tiles);
+  const int64_t max_splits = ceil_div(p.P, (int64_t)PPB * 8);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  p.chunk = ceil_div(ceil_div(p.P, splits), PPB) * PPB;
+  splits = ceil_div(p.P, p.chunk);
+  p.splits = (int)splits;
+  SGB_REQUIRE((int64_t)p.ctiles * p.taps <= 65535 && splits <= 65535, "problem too large for the UMMA wgrad grid");
+  const size_t smem = (size_t)STAGES * (UM * PPB * sizeof(T) + BNC * PPB * sizeof(T)) + 1024;
+  auto kern = conv_wgrad_umma_kernel<T, KIND, BNC, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    SGB_REQUIRE(e == cudaSuccess, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    attr_set = true;
+  }
+  kern<<<dim3((unsigned)p.otiles, (unsigned)(p.ctiles * p.taps), (unsigned)splits), 160, smem, s>>>(p);
+  SGB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <class T, int KIND>
+static int dispatch_wgrad_bn(const sgb_conv_desc* d, const void* x, const void* dy, float* dw, cudaStream_t s) {
+  const int ci = d->ci;
+  if (ci <= 32) return launch_wgrad_umma<T, KIND, 32>(d, x, dy, dw, s);
+  if (ci <= 64) return launch_wgrad_umma<T, KIND, 64>(d, x, dy, dw, s);
+  if (ci <= 128) return launch_wgrad_umma<T, KIND, 128>(d, x, dy, dw, s);
+  return launch_wgrad_umma<T, KIND, 256>(d, x, dy, dw, s);
+}
+
+int conv_wgrad_umma(const sgb_conv_desc* d, const void* x, const void* dy, void* dw, cudaStream_t s) {
+  const int64_t wnum = (int64_t)d->co * d->ci * d->kh * d->kw;
+  cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * wnum, s);
+  SGB_REQUIRE(e == cudaSuccess, "memset failed");
+  if ((int64_t)d->n * d->out_h * d->out_w == 0) return 0;
+  if (d->dtype == SGB_F16) return dispatch_wgrad_bn<__half, 0>(d, x, dy, (float*)dw, s);
+  if (d->dtype == SGB_BF16) return dispatch_wgrad_bn<__nv_bfloat16, 1>(d, x, dy, (float*)dw, s);
+  return dispatch_wgrad_bn<float, 2>(d, x, dy, (float*)dw, s);
 }
 
 }  // namespace sgb

@@ -7,12 +7,15 @@
 //
 // Kernels:
 //   upfirdn2d_generic_kernel  any filter size / up / down / padding / layout (strides), one output per thread.
-//   upfirdn2d_tile_kernel<..> NCHW planes, compile-time (up, down, taps): a CTA stages the input patch of a
-//                             32x(8*ROWS) output tile in shared memory with coalesced loads, the filter lives in
-//                             registers, the polyphase structure of up=2 is resolved at compile time (only
-//                             the (taps/up)^2 live taps are visited), and each thread produces a 1x4 strip.
-//   upfirdn2d_nhwc_kernel<..> channels_last: a thread owns 16 bytes of channels of one output pixel and walks
-//                             the live taps; neighbouring pixels are served by L1/L2.
+//   upfirdn2d_tile_kernel<..> NCHW planes, compile-time (up, down) in {(1,1),(2,1),(1,2)}, filters up to 4x4: a CTA
+//                             stages the input patch of a 64x16 output tile in shared memory with coalesced loads;
+//                             only the live taps of the polyphase structure are visited; lanes walk x so stores coalesce.
+//   upfirdn2d_cl_kernel<..>   channels_last, same (up, down) set: a thread owns 16 bytes of channels (128-bit loads and
+//                             stores) and PX = 4 consecutive output pixels of one row; per live filter row it loads the
+//                             few input pixels those 4 outputs share into registers once (7 / 4 / 10 vectors for
+//                             (1,1) / (2,1) / (1,2)) and applies the taps with compile-time indexing.  CTAs cover
+//                             compact 4-row tiles so the vertical reuse is served by L1.
+#include <type_traits>
 #include "common.cuh"
 
 namespace sgb {
@@ -148,6 +151,87 @@ __global__ void __launch_bounds__(256) upfirdn2d_tile_kernel(UpfirdnParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// channels_last kernel.  blockDim = (CVB, 256 / CVB): x = channel vector, y = (row in tile, x group).
+// PADPAR = padx0 & 1 (only matters for UP == 2: fixes the polyphase pattern at compile time).
+template <class T, int UP, int DOWN, int PADPAR>
+__global__ void __launch_bounds__(256) upfirdn2d_cl_kernel(UpfirdnParams p, int cv_total, int cvb, int txg) {
+  typedef typename Acc<T>::type A;
+  constexpr int VEC = Vec16<T>::N;
+  constexpr int FT = 4, PX = 4, TY = 4;
+  constexpr int NIX = ((PX - 1) * DOWN + FT - 1) / UP + 1;
+  __shared__ float sf[FT * FT];
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  if (tid < FT * FT) {
+    const int ty = tid / FT, tx = tid % FT;
+    float v = 0.f;
+    if (ty < p.fh && tx < p.fw) {
+      const int fy = p.flip ? ty : p.fh - 1 - ty, fx = p.flip ? tx : p.fw - 1 - tx;
+      v = p.f[fy * p.f_sy + fx * p.f_sx] * p.gain;
+    }
+    sf[tid] = v;
+  }
+  __syncthreads();
+
+  const int cchunks = (cv_total + cvb - 1) / cvb;
+  const int n = blockIdx.z / cchunks;
+  const int cv = (blockIdx.z - n * cchunks) * cvb + threadIdx.x;
+  const int ry = threadIdx.y / txg, xg = threadIdx.y - ry * txg;
+  const int oy = blockIdx.y * TY + ry;
+  const int ox0 = (blockIdx.x * txg + xg) * PX;
+  if (cv >= cv_total || oy >= p.out_h || ox0 >= p.out_w) return;
+  const int c0 = cv * VEC;
+
+  A acc[PX][VEC];
+#pragma unroll
+  for (int j = 0; j < PX; j++)
+#pragma unroll
+    for (int e = 0; e < VEC; e++) acc[j][e] = A(0);
+
+  const T* xn = (const T*)p.x + (int64_t)n * p.xs[0] + c0;
+  const int base_y = oy * DOWN - p.pady0;
+  const int ty0 = ((-base_y) % UP + UP) % UP;
+  // first input column any of the PX outputs touches: ceil((ox0*DOWN - padx0) / UP)
+  const int bx = ox0 * DOWN - p.padx0;
+  const int ix_first = (UP == 1) ? bx : ((bx + PADPAR) >> 1);      // UP == 2: bx has parity PADPAR (ox0 is even)
+  for (int ty = ty0; ty < FT; ty += UP) {
+    const int iy = (base_y + ty) / UP;
+    if (iy < 0 || iy >= p.in_h) continue;
+    const float4 fr = *(const float4*)(sf + ty * FT);
+    const float frow[4] = {fr.x, fr.y, fr.z, fr.w};
+    const T* xr = xn + (int64_t)iy * p.xs[2];
+    Vec16<T> in[NIX];
+#pragma unroll
+    for (int i = 0; i < NIX; i++) {
+      const int ix = ix_first + i;
+      in[i].raw = (ix >= 0 && ix < p.in_w) ? __ldg((const uint4*)(xr + (int64_t)ix * p.xs[3])) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int j = 0; j < PX; j++) {
+#pragma unroll
+      for (int tx = 0; tx < FT; tx++) {
+        // position of this tap in the zero-inserted image relative to UP*ix_first
+        const int rel = j * DOWN + tx - ((UP == 2) ? PADPAR : 0);
+        if (UP == 2 && (rel & 1)) continue;          // zero-inserted sample
+        const int i = rel / UP;
+        if (i < 0 || i >= NIX) continue;
+        const A fv = A(frow[tx]);
+#pragma unroll
+        for (int e = 0; e < VEC; e++) acc[j][e] += to_acc<T>(in[i].v[e]) * fv;
+      }
+    }
+  }
+  T* yp = (T*)p.y + (int64_t)n * p.ys[0] + (int64_t)oy * p.ys[2] + c0;
+#pragma unroll
+  for (int j = 0; j < PX; j++) {
+    if (ox0 + j >= p.out_w) break;
+    Vec16<T> o;
+#pragma unroll
+    for (int e = 0; e < VEC; e++) o.v[e] = from_acc<T>(acc[j][e]);
+    *(uint4*)(yp + (int64_t)(ox0 + j) * p.ys[3]) = o.raw;
+  }
+}
+
 }  // namespace sgb
 
 using namespace sgb;
@@ -169,6 +253,27 @@ static int launch_upfirdn(const UpfirdnParams& p, cudaStream_t s) {
     else                            upfirdn2d_tile_kernel<T, 1, 2, 4><<<grid, 256, 0, s>>>(p);
     SGB_LAUNCH_CHECK();
     return 0;
+  }
+  // channels_last kernel: channel-contiguous tensors whose channel count allows 16-byte vectors
+  constexpr int VEC = Vec16<T>::N;
+  const bool cl_ok = sq && small && p.xs[1] == 1 && p.ys[1] == 1 && p.c % VEC == 0 && aligned16(p.x) && aligned16(p.y) &&
+                     p.xs[0] % VEC == 0 && p.xs[2] % VEC == 0 && p.xs[3] % VEC == 0 &&
+                     p.ys[0] % VEC == 0 && p.ys[2] % VEC == 0 && p.ys[3] % VEC == 0 && !std::is_same<T, double>::value;
+  if (cl_ok) {
+    const int cv_total = p.c / VEC;
+    int cvb = 1; while (cvb < cv_total && cvb < 32) cvb <<= 1;
+    const int txg = 256 / cvb / 4;                       // x groups per CTA (4 rows per CTA)
+    const int64_t gx = ceil_div(p.out_w, txg * 4), gy = ceil_div(p.out_h, 4), gz = (int64_t)p.n * ceil_div(cv_total, cvb);
+    if (gy <= 65535 && gz <= 65535) {
+      dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)gz), block(cvb, 256 / cvb);
+      const int pp = p.padx0 & 1;
+      if (p.upx == 1 && p.downx == 1)      upfirdn2d_cl_kernel<T, 1, 1, 0><<<grid, block, 0, s>>>(p, cv_total, cvb, txg);
+      else if (p.upx == 2 && pp == 0)      upfirdn2d_cl_kernel<T, 2, 1, 0><<<grid, block, 0, s>>>(p, cv_total, cvb, txg);
+      else if (p.upx == 2)                 upfirdn2d_cl_kernel<T, 2, 1, 1><<<grid, block, 0, s>>>(p, cv_total, cvb, txg);
+      else                                 upfirdn2d_cl_kernel<T, 1, 2, 0><<<grid, block, 0, s>>>(p, cv_total, cvb, txg);
+      SGB_LAUNCH_CHECK();
+      return 0;
+    }
   }
   int64_t blocks = ceil_div(total, 256);
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;

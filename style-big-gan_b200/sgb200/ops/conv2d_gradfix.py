@@ -70,6 +70,7 @@ def _make_desc(x, y, transposed, ci, co, kh, kw, stride, pad, groups, flip, in_s
     # fp32 tensors: TF32 tensor cores only if the caller allows it the way it would for cuDNN
     # (reference trainers.py:511 sets torch.backends.cudnn.allow_tf32 from perf.allow_tf32)
     d.strict_fp32 = 0 if torch.backends.cudnn.allow_tf32 else 1
+    d.force_simt = 0 if use_tensor_cores else 1
     d.workspace, d.workspace_bytes = None, 0
     return d
 

@@ -114,3 +114,32 @@ def test_umma_gradients_fp16():
         dxo, dwo = torch.autograd.grad(yo, [xo, wo], dy)
         assert_close(dx, dxo, TOL, f'dx up{up} down{down}')
         assert_close(dw, dwo, TOL, f'dw up{up} down{down}')
+
+
+@pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16, torch.float32])
+@pytest.mark.parametrize('case', [
+    # (N, Ci, Co, H, k, stride, pad)
+    (2, 64, 64, 16, 3, 1, 1),
+    (3, 32, 48, 9, 3, 1, 1),          # pixel tail, co/ci tails inside a tile
+    (2, 64, 128, 17, 3, 2, 0),        # stride 2
+    (1, 512, 512, 4, 3, 1, 1),        # several o / c tiles, 16 pixels only
+    (4, 128, 8, 16, 1, 1, 0),         # 1x1, tiny co
+    (2, 72, 264, 8, 3, 1, 1),         # co > 256 with a tail
+])
+def test_umma_wgrad_vs_oracle(dtype, case):
+    from sgb200.ops import conv2d_gradfix as cg
+    n, ci, co, h, k, stride, pad = case
+    torch.manual_seed(5)
+    torch.backends.cudnn.allow_tf32 = True
+    x = _cl(torch.randn(n, ci, h, h).to(DEV, dtype))
+    w = (torch.randn(co, ci, k, k) / math.sqrt(ci * k * k)).to(DEV, dtype).requires_grad_(True)
+    s = (torch.randn(n, ci) + 1).to(DEV)
+    for scale in (None, s):
+        y = cg.conv2d(x, w, stride=stride, padding=pad, in_scale=scale)
+        dy = torch.randn(y.shape).to(DEV, dtype)
+        dw, = torch.autograd.grad(y, [w], dy)
+        xo = x.cpu().float() * (1 if scale is None else scale.cpu()[:, :, None, None])
+        wo = w.detach().cpu().float().requires_grad_(True)
+        yo = torch.nn.functional.conv2d(xo, wo, stride=stride, padding=pad)
+        dwo, = torch.autograd.grad(yo, [wo], dy.cpu().float())
+        assert_close(dw, dwo, TOL, f'{case} {dtype} scale={scale is not None}')

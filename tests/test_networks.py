@@ -70,14 +70,14 @@ def test_forward_matches_reference_golden(gold, channels_last):
 
 
 def _check(z, phase, tag, module, tol):
-    """Per-tensor max-norm relative error.  Tensors whose reference gradient is more than 1000x smaller than
+    """Per-tensor max-norm relative error.  Tensors whose reference gradient is more than 100x smaller than
     the phase's largest one (e.g. D biases under R1: they only receive second-order signal through the
     minibatch-stddev layer, ~1e-8 against 1e-2 for the weights) are measured against that floor instead of
     their own tiny norm, where fp32 summation order alone exceeds any relative tolerance."""
     keys = [k for k in z.files if k.startswith(f'{phase}.grad.{tag}')]
     assert keys
     named = dict(module.named_parameters())
-    floor = 1e-3 * max(float(np.abs(z[k]).max()) for k in keys)
+    floor = 1e-2 * max(float(np.abs(z[k]).max()) for k in keys)
     for k in keys:
         name = k[len(f'{phase}.grad.{tag}'):]
         assert named[name].grad is not None, f'{phase}: no grad for {name}'
