@@ -92,7 +92,7 @@ def test_bias_act_shapes_dtypes(ops, dtype, shape, dim, cl, act, gain, clamp):
     if clamp is not None and dtype in (torch.float16, torch.bfloat16):
         pre = R.bias_act(xo.detach(), bo.detach(), dim=dim, act=act, gain=gain, clamp=None).abs()
         safe = (pre - clamp).abs() > 4 * torch.finfo(dtype).eps * clamp
-        assert safe.float().mean() > 0.99
+        assert safe.float().mean() > 0.95
     assert_close(dx.detach().cpu().to(od) * safe, dxo * safe, tol, 'dx')
     if bool(safe.all()):
         assert_close(db, dbo, 2 * tol if dtype not in (torch.float16, torch.bfloat16) else 3e-2, 'db')
