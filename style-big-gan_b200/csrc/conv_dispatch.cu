@@ -8,6 +8,8 @@ int conv_wgrad_simt(const sgb_conv_desc* d, const void* x, const void* dy, void*
 bool conv_umma_eligible(const sgb_conv_desc* d);
 int conv_forward_umma(const sgb_conv_desc* d, const void* x, const void* w, void* y, cudaStream_t s);
 bool conv_wgrad_umma_eligible(const sgb_conv_desc* d);
+bool conv_halo_eligible(const sgb_conv_desc* d);
+int conv_forward_halo(const sgb_conv_desc* d, const void* x, const void* w, void* y, cudaStream_t s);
 int conv_wgrad_umma(const sgb_conv_desc* d, const void* x, const void* dy, void* dw, cudaStream_t s);
 
 static int validate(const sgb_conv_desc* d) {
@@ -40,7 +42,10 @@ extern "C" int sgb_conv2d_forward(const sgb_conv_desc* d, const void* x, const v
   if ((int64_t)d->n * d->out_h * d->out_w == 0) return 0;
   SGB_REQUIRE(x && w && y, "x, w and y must not be NULL");
   cudaStream_t s = (cudaStream_t)stream;
-  if (conv_umma_eligible(d)) return conv_forward_umma(d, x, w, y, s);
+  if (conv_umma_eligible(d)) {
+    if (d->force_simt != 2 && conv_halo_eligible(d)) return conv_forward_halo(d, x, w, y, s);
+    return conv_forward_umma(d, x, w, y, s);
+  }
   return conv_forward_simt(d, x, w, y, s);
 }
 

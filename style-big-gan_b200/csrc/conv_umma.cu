@@ -22,10 +22,10 @@
 // conv_transpose2d, any kernel size / stride / padding, groups == 1.
 #include "common.cuh"
 #include "act.cuh"
+#include "umma.cuh"
 
 namespace sgb {
 
-constexpr int UM = 128;          // pixels per CTA tile (UMMA M)
 constexpr int KB_BYTES = 128;    // bytes of K per block per row (8 chunks of 16 B)
 constexpr int A_STAGE_BYTES = UM * KB_BYTES;   // 16 KB
 constexpr int NUM_PRODUCERS = 128;
@@ -38,95 +38,6 @@ struct UmmaParams {
   int tc;               // elements per 16-byte chunk
   int vec_store;        // co allows 16-byte stores
 };
-
-// ---- PTX wrappers -------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}"
-      :: "r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(dst_smem), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(addr), "r"(cols) : "memory");
-}
-
-template <int KIND>
-__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  if (KIND == 2) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                 :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-  } else {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                 :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-  }
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
-}
-
-// 32 lanes x 16 consecutive fp32 columns
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-               : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major, no-swizzle shared-memory matrix descriptor: core matrices of 8 rows x 16 bytes (128 contiguous bytes);
-// SBO = distance between 8-row groups, LBO = distance between the 16-byte K chunks.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;            // descriptor version (sm_100)
-  return d;                           // base_offset = 0, lbo_mode = 0, layout_type = 0 (no swizzle)
-}
-
-// instruction descriptor: fp32 accumulate, A/B format, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int kind, int n, int mn_major = 0) {
-  return (1u << 4) | ((uint32_t)kind << 7) | ((uint32_t)kind << 10) | ((uint32_t)mn_major << 15) | ((uint32_t)mn_major << 16) |
-         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
-}
-
-__device__ __forceinline__ uint32_t f32_to_tf32(float v) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-  return r;
-}
 
 // ---- weight re-pack ------------------------------------------------------------------------------------
 // out image per (ntile, tap, cblock): [chunk j (8)][row r (BN)][16 bytes]; zero outside (co, ci).
@@ -535,7 +446,7 @@ __global__ void __launch_bounds__(160, 1) conv_wgrad_umma_kernel(WgradParams p) 
 }
 
 // ---- host side -------------------------------------------------------------------------------------------
-static int pick_bn(int co) {
+int pick_bn(int co) {
   if (co <= 16) return 16;
   if (co <= 32) return 32;
   if (co <= 64) return 64;
@@ -544,12 +455,25 @@ static int pick_bn(int co) {
 }
 static int stages_for(int bn) { return bn == 256 ? 4 : (bn == 128 ? 3 : 4); }
 
-static int elem_size(int dtype) { return dtype == SGB_F32 ? 4 : 2; }
+int elem_size(int dtype) { return dtype == SGB_F32 ? 4 : 2; }
+
+// re-pack w into d->workspace as B-tile images for N tiles of `bn` channels (order [ntile][tap][cblock])
+int pack_weights_umma(const sgb_conv_desc* d, const void* w, int bn, cudaStream_t s) {
+  const int tc = 16 / elem_size(d->dtype);
+  const int ntiles = (d->co + bn - 1) / bn, cblocks = (d->ci + 8 * tc - 1) / (8 * tc);
+  const int64_t total = (int64_t)ntiles * d->kh * d->kw * cblocks * 8 * bn * tc;
+  int64_t blocks = ceil_div(total, 256); if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  if (d->dtype == SGB_F16)       pack_weights_kernel<__half, 0><<<(unsigned)blocks, 256, 0, s>>>((const __half*)w, d->workspace, *d, bn, ntiles, cblocks, tc);
+  else if (d->dtype == SGB_BF16) pack_weights_kernel<__nv_bfloat16, 1><<<(unsigned)blocks, 256, 0, s>>>((const __nv_bfloat16*)w, d->workspace, *d, bn, ntiles, cblocks, tc);
+  else                           pack_weights_kernel<float, 2><<<(unsigned)blocks, 256, 0, s>>>((const float*)w, d->workspace, *d, bn, ntiles, cblocks, tc);
+  SGB_LAUNCH_CHECK();
+  return 0;
+}
 
 bool conv_umma_eligible(const sgb_conv_desc* d) {
   if (d->dtype != SGB_F32 && d->dtype != SGB_F16 && d->dtype != SGB_BF16) return false;
   if (d->dtype == SGB_F32 && d->strict_fp32) return false;
-  if (d->force_simt) return false;
+  if (d->force_simt == 1) return false;
   if (d->groups != 1) return false;
   const int tc = 16 / elem_size(d->dtype);
   if (d->ci % tc != 0) return false;
@@ -571,12 +495,7 @@ static int launch_umma(const sgb_conv_desc* d, const void* x, const void* w, voi
   p.vec_store = (d->co % TC == 0 && y_al) ? 1 : 0;
   SGB_REQUIRE(aligned16(x) && aligned16(d->workspace), "x and workspace must be 16-byte aligned");
   // 1) re-pack the weights into B-tile images
-  {
-    const int64_t total = (int64_t)p.ntiles * p.taps * p.cblocks * 8 * BN * TC;
-    int64_t blocks = ceil_div(total, 256); if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-    pack_weights_kernel<T, KIND><<<(unsigned)blocks, 256, 0, s>>>((const T*)w, d->workspace, *d, BN, p.ntiles, p.cblocks, TC);
-    SGB_LAUNCH_CHECK();
-  }
+  if (int r = pack_weights_umma(d, w, BN, s)) return r;
   // 2) implicit GEMM
   const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + BN * KB_BYTES) + 1024;
   auto kern = conv_umma_kernel<T, KIND, BN, STAGES>;
@@ -614,7 +533,7 @@ int conv_forward_umma(const sgb_conv_desc* d, const void* x, const void* w, void
 bool conv_wgrad_umma_eligible(const sgb_conv_desc* d) {
   if (d->dtype != SGB_F32 && d->dtype != SGB_F16 && d->dtype != SGB_BF16) return false;
   if (d->dtype == SGB_F32 && d->strict_fp32) return false;
-  if (d->force_simt) return false;
+  if (d->force_simt == 1) return false;
   if (d->groups != 1 || d->transposed) return false;
   const int tc = 16 / elem_size(d->dtype);
   if (d->ci % tc != 0 || d->co % tc != 0) return false;

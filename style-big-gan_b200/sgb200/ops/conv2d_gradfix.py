@@ -19,6 +19,7 @@ from .. import _lib
 
 enabled = True                      # kept for API compatibility; the custom op is the only implementation
 use_tensor_cores = True             # False routes every convolution to the SIMT kernels (debugging / A-B tests)
+use_halo_kernel = True              # False keeps tensor cores but skips the halo-tile kernel (A-B tests)
 weight_gradients_disabled = False   # forcefully disable computation of gradients with respect to the weights
 
 
@@ -70,7 +71,7 @@ def _make_desc(x, y, transposed, ci, co, kh, kw, stride, pad, groups, flip, in_s
     # fp32 tensors: TF32 tensor cores only if the caller allows it the way it would for cuDNN
     # (reference trainers.py:511 sets torch.backends.cudnn.allow_tf32 from perf.allow_tf32)
     d.strict_fp32 = 0 if torch.backends.cudnn.allow_tf32 else 1
-    d.force_simt = 0 if use_tensor_cores else 1
+    d.force_simt = (0 if use_halo_kernel else 2) if use_tensor_cores else 1
     d.workspace, d.workspace_bytes = None, 0
     return d
 

@@ -143,3 +143,43 @@ def test_umma_wgrad_vs_oracle(dtype, case):
         yo = torch.nn.functional.conv2d(xo, wo, stride=stride, padding=pad)
         dwo, = torch.autograd.grad(yo, [wo], dy.cpu().float())
         assert_close(dw, dwo, TOL, f'{case} {dtype} scale={scale is not None}')
+
+
+@pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16, torch.float32])
+@pytest.mark.parametrize('case', [
+    # (N, Ci, Co, H, W, k, pad, transposed)   -- stride 1, W % 8 == 0 => halo-tile kernel
+    (1, 64, 64, 16, 16, 3, 1, False),
+    (3, 64, 64, 8, 8, 3, 1, False),           # tiles straddle images (virtual rows)
+    (2, 32, 48, 24, 16, 3, 1, False),         # H not a multiple of 16, co tail
+    (2, 136, 24, 16, 8, 3, 1, False),         # K tail (136 = 2*64 + 8)
+    (2, 128, 64, 16, 16, 3, 1, True),         # dgrad form
+    (2, 64, 64, 16, 16, 3, 0, True),          # transposed, pad 0 (output grows by 2)
+    (2, 64, 64, 18, 18, 3, 0, False),         # valid conv: out 16x16
+    (2, 64, 3, 16, 16, 1, 0, False),          # toRGB
+    (1, 512, 512, 8, 8, 3, 1, False),         # two N tiles
+    (1, 64, 272, 16, 16, 1, 0, False),
+    (5, 64, 64, 32, 32, 3, 1, False),
+])
+def test_halo_conv_vs_oracle_and_v1(dtype, case):
+    from sgb200.ops import conv2d_gradfix as cg
+    n, ci, co, h, wd, k, pad, tr = case
+    torch.manual_seed(11)
+    torch.backends.cudnn.allow_tf32 = True
+    x = _cl(torch.randn(n, ci, h, wd).to(DEV, dtype))
+    wshape = (ci, co, k, k) if tr else (co, ci, k, k)
+    w = (torch.randn(wshape) / math.sqrt(ci * k * k)).to(DEV, dtype)
+    s = (torch.randn(n, ci) + 1).to(DEV)
+    op = cg.conv_transpose2d if tr else cg.conv2d
+    fo = torch.nn.functional.conv_transpose2d if tr else torch.nn.functional.conv2d
+    for scale in ((None, s) if not tr else (None,)):
+        y = op(x, w, padding=pad, in_scale=scale)
+        xo = x.cpu().float() * (1 if scale is None else scale.cpu()[:, :, None, None])
+        yo = fo(xo, w.cpu().float(), padding=pad)
+        assert y.shape == yo.shape
+        assert_close(y, yo, TOL, f'{case} {dtype} halo scale={scale is not None}')
+        cg.use_halo_kernel = False
+        try:
+            y1 = op(x, w, padding=pad, in_scale=scale)
+        finally:
+            cg.use_halo_kernel = True
+        assert_close(y, y1.float().cpu(), 2e-3 if dtype != torch.float32 else 1e-3, f'{case} {dtype} halo vs per-tap kernel')
