@@ -1,5 +1,5 @@
-// tcgen05 implicit-GEMM convolution, "halo tile" variant for stride-1 convolutions (conv2d and conv_transpose2d,
-// i.e. forward and data-gradient of every 3x3 / 1x1 layer), channels_last.
+// tcgen05 implicit-GEMM convolution, persistent "halo tile" kernel for stride-1 convolutions (conv2d and
+// conv_transpose2d, i.e. forward and data-gradient of every 3x3 / 1x1 layer), channels_last.
 //
 // conv_umma.cu re-gathers the A operand once per filter tap (9x the activation traffic through LSU + shared
 // memory).  Here the CTA stages the input patch of its output tile ONCE per channel block and the nine taps are nine
@@ -14,10 +14,14 @@
 // Rows are "virtual rows": every image contributes out_h + kh - 1 rows (its zero padding included), so tiles may
 // straddle images with one uniform addressing scheme; the kh - 1 junk rows per image are computed and dropped.
 //
-// Roles (192 threads): warps 0-3 stage patches (16-byte chunks, 8 threads per pixel => 128-byte coalesced global
-// reads; patch pitch padded so the 8 chunk planes hit different banks) and run the epilogue; warp 4 issues
-// tcgen05.mma and owns TMEM; warp 5 streams the pre-packed weight tiles with cp.async.bulk.
-// Pipelines: A ring (SA patches), B ring (SB weight tiles), one TMEM accumulator.
+// Persistent: grid = #SMs, each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  Ten warps:
+//   warps 0-3  epilogue: tcgen05.ld of accumulator buffer (t & 1), demod scale / noise / bias_act, 128-bit stores,
+//              release the buffer (acc_empty) -- runs while the next tile's MMAs fill the other buffer
+//   warp 4     MMA issuer (one lane): tcgen05.mma.cta_group::1, 4 per (channel block, tap); owns TMEM (2*BN columns)
+//   warp 5     weight loader: cp.async.bulk of pre-packed B tiles into a ring of SB stages
+//   warps 6-9  patch producers: cp.async 16-byte chunks global -> shared (zero-fill for padding), several patches in
+//              flight per thread (LOOKAHEAD), optional in-place style scaling, fence.proxy.async, mbarrier arrive
+// so the HBM latency of tile t+1 / t+2 hides behind the MMAs and the epilogue of tile t.
 #include "common.cuh"
 #include "act.cuh"
 #include "umma.cuh"
@@ -26,6 +30,8 @@ namespace sgb {
 
 constexpr int TILE_H = 16, TILE_W = 8;
 constexpr int KB_BYTES_H = 128;
+constexpr int HALO_THREADS = 320;
+constexpr int LOOKAHEAD = 2;             // patches in flight per producer thread beyond the one being published
 
 struct HaloParams {
   sgb_conv_desc d;
@@ -33,31 +39,37 @@ struct HaloParams {
   int VR;               // virtual rows per image = out_h + kh - 1
   int HR, HC;           // patch rows / cols
   int top, left;        // padded-to-actual offsets
-  int row_tiles, col_tiles;
+  int row_tiles, col_tiles, ntiles;
+  int64_t total_tiles;
   int taps, cblocks;
   int lbo;              // bytes between channel chunks of the patch (padded)
   int a_stage_bytes;
   int vec_store;
 };
 
+__device__ __forceinline__ void decode_tile(const HaloParams& p, int64_t t, int& ntile, int& u0, int& x0) {
+  ntile = (int)(t % p.ntiles);
+  const int64_t mt = t / p.ntiles;
+  x0 = (int)(mt % p.col_tiles) * TILE_W;
+  u0 = (int)(mt / p.col_tiles) * TILE_H;
+}
+
 template <class T, int KIND, int BN, int SA, int SB>
-__global__ void __launch_bounds__(192, 1) conv_halo_kernel(HaloParams p) {
+__global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(HaloParams p) {
   constexpr int TC = 16 / sizeof(T);
   constexpr int BK = 8 * TC;
   constexpr int B_STAGE_BYTES = BN * KB_BYTES_H;
-  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   constexpr uint32_t IDESC = make_idesc(KIND, BN);
   constexpr int MAX_SLOTS = 12;                      // ceil(18*10*8 / 128)
+  static_assert(SA > LOOKAHEAD, "need more patch stages than patches in flight");
 
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t a_full[SA], a_empty[SA], b_full[SB], b_empty[SB], accum_bar;
+  __shared__ uint64_t a_full[SA], a_empty[SA], b_full[SB], b_empty[SB], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_slot;
 
   const sgb_conv_desc& d = p.d;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ntile = blockIdx.y;
-  const int col_tile = blockIdx.x % p.col_tiles, row_tile = blockIdx.x / p.col_tiles;
-  const int u0 = row_tile * TILE_H, x0 = col_tile * TILE_W;
   uint8_t* a_base = smem;
   uint8_t* b_base = smem + SA * p.a_stage_bytes;
 
@@ -65,7 +77,7 @@ __global__ void __launch_bounds__(192, 1) conv_halo_kernel(HaloParams p) {
     if (lane == 0) {
       for (int s = 0; s < SA; s++) { mbar_init(smem_u32(&a_full[s]), 128); mbar_init(smem_u32(&a_empty[s]), 1); }
       for (int s = 0; s < SB; s++) { mbar_init(smem_u32(&b_full[s]), 1); mbar_init(smem_u32(&b_empty[s]), 1); }
-      mbar_init(smem_u32(&accum_bar), 1);
+      for (int s = 0; s < 2; s++) { mbar_init(smem_u32(&acc_full[s]), 1); mbar_init(smem_u32(&acc_empty[s]), 4); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -76,184 +88,223 @@ __global__ void __launch_bounds__(192, 1) conv_halo_kernel(HaloParams p) {
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
-  if (warp < 4) {
-    // =========================== patch producers ===========================
-    const int t = threadIdx.x;
+  if (warp >= 6) {
+    // =========================== patch producers (cp.async) ===========================
+    const int t = threadIdx.x - 192;
     const int j = t & 7;                               // channel chunk owned by this thread
     const int npix = p.HR * p.HC;
-    // per-slot source offsets (elements) of the patch pixels this thread stages; -1 = zero (padding / outside)
-    // (int32: the launcher only takes this path when the input has fewer than 2^31 elements)
-    int off[MAX_SLOTS];
-    int soff[MAX_SLOTS];                               // in_scale row (n * ci)
     const uint32_t dst0 = (uint32_t)(j * p.lbo + (t >> 3) * 16);   // slot i lands at dst0 + i * 256
-#pragma unroll
-    for (int i = 0; i < MAX_SLOTS; i++) {
-      const int pix = (t >> 3) + 16 * i;
-      off[i] = -1; soff[i] = 0;
-      if (pix < npix) {
-        const int hr = pix / p.HC, hc = pix - hr * p.HC;
-        const int u = u0 + hr;
-        const int n = u / p.VR;
-        const int iy = u - n * p.VR - p.top;
-        const int ix = x0 + hc - p.left;
-        if (n < d.n && iy >= 0 && iy < d.in_h && ix >= 0 && ix < d.in_w) {
-          off[i] = (int)(n * d.x_strides[0] + iy * d.x_strides[2] + ix * d.x_strides[3]);
-          soff[i] = n * d.ci;
-        }
-      }
-    }
     const T* xb = (const T*)p.x;
     const float* scb = (const float*)d.in_scale;
-    for (int cb = 0; cb < p.cblocks; cb++) {
-      const int sa = cb % SA;
-      const uint32_t ph = (cb / SA) & 1;
-      const int c = cb * BK + j * TC;
-      const bool c_ok = c < d.ci;
-      uint4 v[MAX_SLOTS];
-#pragma unroll
-      for (int i = 0; i < MAX_SLOTS; i++)
-        v[i] = (c_ok && off[i] >= 0) ? __ldg((const uint4*)(xb + off[i] + c)) : make_uint4(0, 0, 0, 0);
+    int pa = 0;                                        // patches issued so far (ring position)
+    int pub = 0;                                       // patches published so far
+
+    auto publish = [&](int idx) {                      // patch number idx has landed: optional scaling, fence, arrive
+      const int sa = idx % SA;
       if (scb) {
-#pragma unroll
-        for (int i = 0; i < MAX_SLOTS; i++) {
-          if (c_ok && off[i] >= 0) {
-            const float* sp = scb + soff[i] + c;
+        uint8_t* dst = a_base + sa * p.a_stage_bytes;
+        // which tile / channel block was patch number idx?  (same walk as the issue loop below)
+        int nt_, u0o, x0_;
+        decode_tile(p, (int64_t)blockIdx.x + (int64_t)(idx / p.cblocks) * gridDim.x, nt_, u0o, x0_);
+        const int co = (idx % p.cblocks) * BK + j * TC;
+        if (co < d.ci) {
+#pragma unroll 1
+          for (int i = 0; i < MAX_SLOTS; i++) {
+            const int pix = (t >> 3) + 16 * i;
+            if (pix >= npix) break;
+            int n = (u0o + pix / p.HC) / p.VR;
+            n = n < d.n ? n : d.n - 1;
+            const float* sp = scb + (int64_t)n * d.ci + co;
+            uint4* q = (uint4*)(dst + dst0 + i * 256);
+            uint4 v = *q;
             if (KIND == 2) {
               const float4 s4 = __ldg((const float4*)sp);
-              float* f = (float*)&v[i];
+              float* f = (float*)&v;
               f[0] *= s4.x; f[1] *= s4.y; f[2] *= s4.z; f[3] *= s4.w;
             } else {
               const float4 sa4 = __ldg((const float4*)sp), sb4 = __ldg((const float4*)(sp + 4));
               const float sv[8] = {sa4.x, sa4.y, sa4.z, sa4.w, sb4.x, sb4.y, sb4.z, sb4.w};
-              T* h = (T*)&v[i];
+              T* h = (T*)&v;
 #pragma unroll
               for (int e = 0; e < 8; e++) h[e] = from_acc<T>(to_acc<T>(h[e]) * sv[e]);
             }
+            *q = v;
           }
         }
       }
-      if (KIND == 2) {
-#pragma unroll
-        for (int i = 0; i < MAX_SLOTS; i++) {
-          float* f = (float*)&v[i]; uint32_t* u = (uint32_t*)&v[i];
-          u[0] = f32_to_tf32(f[0]); u[1] = f32_to_tf32(f[1]); u[2] = f32_to_tf32(f[2]); u[3] = f32_to_tf32(f[3]);
-        }
-      }
-      mbar_wait(smem_u32(&a_empty[sa]), ph ^ 1);
-      uint8_t* dst = a_base + sa * p.a_stage_bytes;
-#pragma unroll
-      for (int i = 0; i < MAX_SLOTS; i++)
-        if ((t >> 3) + 16 * i < npix) *(uint4*)(dst + dst0 + i * 256) = v[i];
       fence_proxy_async();
       mbar_arrive(smem_u32(&a_full[sa]));
-    }
+    };
 
-    // =========================== epilogue ===========================
-    mbar_wait(smem_u32(&accum_bar), 0);
-    tc_fence_after();
-    const int m = threadIdx.x;                         // TMEM lane = tile row
-    const int ty = m >> 3, tx = m & 7;
-    const int u = u0 + ty;
-    const int n = u / p.VR;
-    const int oy = u - n * p.VR;
-    const int ox = x0 + tx;
-    const bool row_ok = n < d.n && oy < d.out_h && ox < d.out_w;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const float* out_scale = (d.out_scale && row_ok) ? (const float*)d.out_scale + (int64_t)n * d.co : nullptr;
-    const float nz = (d.noise && row_ok) ? ((const float*)d.noise)[((int64_t)n * d.out_h + oy) * d.out_w + ox] : 0.f;
-    const float alpha = d.alpha, gain = d.gain, clamp = d.clamp;
-    T* yrow = (T*)p.y + (int64_t)n * d.y_strides[0] + (int64_t)oy * d.y_strides[2] + (int64_t)ox * d.y_strides[3];
-    const int o_base = ntile * BN;
-#pragma unroll 1
-    for (int cc = 0; cc < BN; cc += 16) {
-      uint32_t acc[16];
-      tmem_ld16(lane_addr + cc, acc);
-      if (!row_ok) continue;
-      float val[16];
+    for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int ntile, u0, x0;
+      decode_tile(p, tile, ntile, u0, x0);
+      // per-slot source offsets (elements) of the patch pixels this thread stages; -1 = zero (padding / outside)
+      int off[MAX_SLOTS];
 #pragma unroll
-      for (int e = 0; e < 16; e++) {
-        const int o = o_base + cc + e;
-        float a = __uint_as_float(acc[e]);
-        if (o < d.co) {
-          if (out_scale) a *= out_scale[o];
-          a += nz;
-          if (d.act) {
-            if (d.bias) a += to_acc<T>(((const T*)d.bias)[o]);
-            a = act_forward<float>(d.act, a, alpha, gain, clamp);
-          }
+      for (int i = 0; i < MAX_SLOTS; i++) {
+        const int pix = (t >> 3) + 16 * i;
+        off[i] = -1;
+        if (pix < npix) {
+          const int hr = pix / p.HC, hc = pix - hr * p.HC;
+          const int u = u0 + hr;
+          const int n = u / p.VR;
+          const int iy = u - n * p.VR - p.top;
+          const int ix = x0 + hc - p.left;
+          if (n < d.n && iy >= 0 && iy < d.in_h && ix >= 0 && ix < d.in_w)
+            off[i] = (int)(n * d.x_strides[0] + iy * d.x_strides[2] + ix * d.x_strides[3]);
         }
-        val[e] = a;
       }
-      if (p.vec_store) {
+      for (int cb = 0; cb < p.cblocks; cb++, pa++) {
+        const int sa = pa % SA;
+        const int c = cb * BK + j * TC;
+        const bool c_ok = c < d.ci;
+        mbar_wait(smem_u32(&a_empty[sa]), ((pa / SA) & 1) ^ 1);
+        const uint32_t dst = smem_u32(a_base + sa * p.a_stage_bytes) + dst0;
 #pragma unroll
-        for (int g = 0; g < 16 / TC; g++) {
-          const int o = o_base + cc + g * TC;
-          if (o < d.co) {
-            Vec16<T> pk;
-#pragma unroll
-            for (int e = 0; e < TC; e++) pk.v[e] = from_acc<T>(val[g * TC + e]);
-            *(uint4*)(yrow + o) = pk.raw;
+        for (int i = 0; i < MAX_SLOTS; i++) {
+          if ((t >> 3) + 16 * i < npix) {
+            const bool ok = c_ok && off[i] >= 0;
+            cp_async16(dst + i * 256, ok ? (const void*)(xb + off[i] + c) : (const void*)xb, ok ? 16u : 0u);
           }
         }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 16; e++) {
-          const int o = o_base + cc + e;
-          if (o < d.co) yrow[(int64_t)o * d.y_strides[1]] = from_acc<T>(val[e]);
+        cp_async_commit();
+        if (pa - pub >= LOOKAHEAD) {                   // keep LOOKAHEAD patches in flight, publish the oldest
+          cp_async_wait<LOOKAHEAD>();
+          publish(pub++);
         }
       }
     }
-    tc_fence_before();
+    cp_async_wait<0>();
+    while (pub < pa) publish(pub++);
   } else if (warp == 4) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
-      int kb = 0;
-      for (int cb = 0; cb < p.cblocks; cb++) {
-        const int sa = cb % SA;
-        mbar_wait(smem_u32(&a_full[sa]), (cb / SA) & 1);
+      int pa = 0, kb = 0, li = 0;
+      for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, li++) {
+        const int buf = li & 1;
+        mbar_wait(smem_u32(&acc_empty[buf]), ((li >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(a_base + sa * p.a_stage_bytes);
-        for (int tap = 0; tap < p.taps; tap++, kb++) {
-          const int sb = kb % SB;
-          mbar_wait(smem_u32(&b_full[sb]), (kb / SB) & 1);
+        const uint32_t tmem_d = tmem_base + buf * BN;
+        int first = 1;
+        for (int cb = 0; cb < p.cblocks; cb++, pa++) {
+          const int sa = pa % SA;
+          mbar_wait(smem_u32(&a_full[sa]), (pa / SA) & 1);
           tc_fence_after();
-          const int ky = tap / d.kw, kx = tap - ky * d.kw;
-          const int pr = d.transposed ? (d.kh - 1 - ky) : ky;        // patch row / col offset of this tap
-          const int pc = d.transposed ? (d.kw - 1 - kx) : kx;
-          const uint32_t a_tap = a_addr + (uint32_t)(pr * p.HC + pc) * 16;
-          const uint32_t b_addr = smem_u32(b_base + sb * B_STAGE_BYTES);
+          const uint32_t a_addr = smem_u32(a_base + sa * p.a_stage_bytes);
+          for (int tap = 0; tap < p.taps; tap++, kb++) {
+            const int sb = kb % SB;
+            mbar_wait(smem_u32(&b_full[sb]), (kb / SB) & 1);
+            tc_fence_after();
+            const int ky = tap / d.kw, kx = tap - ky * d.kw;
+            const int pr = d.transposed ? (d.kh - 1 - ky) : ky;        // patch row / col offset of this tap
+            const int pc = d.transposed ? (d.kw - 1 - kx) : kx;
+            const uint32_t a_tap = a_addr + (uint32_t)(pr * p.HC + pc) * 16;
+            const uint32_t b_addr = smem_u32(b_base + sb * B_STAGE_BYTES);
 #pragma unroll
-          for (int kk = 0; kk < 4; kk++) {
-            const uint64_t adesc = make_smem_desc(a_tap + kk * 2 * p.lbo, p.lbo, p.HC * 16);
-            const uint64_t bdesc = make_smem_desc(b_addr + kk * 2 * (BN * 16), BN * 16, 128);
-            umma<KIND>(tmem_base, adesc, bdesc, IDESC, (kb > 0 || kk > 0) ? 1u : 0u);
+            for (int kk = 0; kk < 4; kk++) {
+              const uint64_t adesc = make_smem_desc(a_tap + kk * 2 * p.lbo, p.lbo, p.HC * 16);
+              const uint64_t bdesc = make_smem_desc(b_addr + kk * 2 * (BN * 16), BN * 16, 128);
+              umma<KIND>(tmem_d, adesc, bdesc, IDESC, first ? 0u : 1u);
+              first = 0;
+            }
+            umma_commit(smem_u32(&b_empty[sb]));
           }
-          umma_commit(smem_u32(&b_empty[sb]));
+          umma_commit(smem_u32(&a_empty[sa]));
         }
-        umma_commit(smem_u32(&a_empty[sa]));
+        umma_commit(smem_u32(&acc_full[buf]));
       }
-      umma_commit(smem_u32(&accum_bar));
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // =========================== weight loader ===========================
+    if (lane == 0) {
+      int kb = 0;
+      for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int ntile = (int)(tile % p.ntiles);
+        const uint8_t* wsrc = (const uint8_t*)p.wpack + (int64_t)ntile * p.taps * p.cblocks * B_STAGE_BYTES;
+        for (int cb = 0; cb < p.cblocks; cb++) {
+          for (int tap = 0; tap < p.taps; tap++, kb++) {
+            const int sb = kb % SB;
+            mbar_wait(smem_u32(&b_empty[sb]), ((kb / SB) & 1) ^ 1);
+            const uint32_t bar = smem_u32(&b_full[sb]);
+            mbar_arrive_expect_tx(bar, B_STAGE_BYTES);
+            bulk_copy_g2s(smem_u32(b_base + sb * B_STAGE_BYTES), wsrc + ((int64_t)tap * p.cblocks + cb) * B_STAGE_BYTES,
+                          B_STAGE_BYTES, bar);
+          }
+        }
+      }
     }
     __syncwarp();
   } else {
-    // =========================== weight loader ===========================
-    if (lane == 0) {
-      const uint8_t* wsrc = (const uint8_t*)p.wpack + (int64_t)ntile * p.taps * p.cblocks * B_STAGE_BYTES;
-      int kb = 0;
-      for (int cb = 0; cb < p.cblocks; cb++) {
-        for (int tap = 0; tap < p.taps; tap++, kb++) {
-          const int sb = kb % SB;
-          mbar_wait(smem_u32(&b_empty[sb]), ((kb / SB) & 1) ^ 1);
-          const uint32_t bar = smem_u32(&b_full[sb]);
-          mbar_arrive_expect_tx(bar, B_STAGE_BYTES);
-          bulk_copy_g2s(smem_u32(b_base + sb * B_STAGE_BYTES), wsrc + ((int64_t)tap * p.cblocks + cb) * B_STAGE_BYTES,
-                        B_STAGE_BYTES, bar);
+    // =========================== epilogue (warps 0-3) ===========================
+    const int m = threadIdx.x;                         // TMEM lane = tile row
+    const int ty = m >> 3, tx = m & 7;
+    const float alpha = d.alpha, gain = d.gain, clamp = d.clamp;
+    int li = 0;
+    for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, li++) {
+      int ntile, u0, x0;
+      decode_tile(p, tile, ntile, u0, x0);
+      const int buf = li & 1;
+      const int u = u0 + ty;
+      const int n = u / p.VR;
+      const int oy = u - n * p.VR;
+      const int ox = x0 + tx;
+      const bool row_ok = n < d.n && oy < d.out_h && ox < d.out_w;
+      const float* out_scale = (d.out_scale && row_ok) ? (const float*)d.out_scale + (int64_t)n * d.co : nullptr;
+      const float nz = (d.noise && row_ok) ? ((const float*)d.noise)[((int64_t)n * d.out_h + oy) * d.out_w + ox] : 0.f;
+      T* yrow = (T*)p.y + (int64_t)n * d.y_strides[0] + (int64_t)oy * d.y_strides[2] + (int64_t)ox * d.y_strides[3];
+      const int o_base = ntile * BN;
+      mbar_wait(smem_u32(&acc_full[buf]), (li >> 1) & 1);
+      tc_fence_after();
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * BN;
+#pragma unroll 1
+      for (int cc = 0; cc < BN; cc += 16) {
+        uint32_t acc[16];
+        tmem_ld16(lane_addr + cc, acc);
+        if (!row_ok) continue;
+        float val[16];
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+          const int o = o_base + cc + e;
+          float a = __uint_as_float(acc[e]);
+          if (o < d.co) {
+            if (out_scale) a *= out_scale[o];
+            a += nz;
+            if (d.act) {
+              if (d.bias) a += to_acc<T>(((const T*)d.bias)[o]);
+              a = act_forward<float>(d.act, a, alpha, gain, clamp);
+            }
+          }
+          val[e] = a;
+        }
+        if (p.vec_store) {
+#pragma unroll
+          for (int g = 0; g < 16 / TC; g++) {
+            const int o = o_base + cc + g * TC;
+            if (o < d.co) {
+              Vec16<T> pk;
+#pragma unroll
+              for (int e = 0; e < TC; e++) pk.v[e] = from_acc<T>(val[g * TC + e]);
+              *(uint4*)(yrow + o) = pk.raw;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; e++) {
+            const int o = o_base + cc + e;
+            if (o < d.co) yrow[(int64_t)o * d.y_strides[1]] = from_acc<T>(val[e]);
+          }
         }
       }
+      // all TMEM reads of this warp are complete (tmem_ld16 waits): hand the buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
     }
-    __syncwarp();
   }
 
+  tc_fence_before();
   __syncthreads();
   if (warp == 4) {
     tc_fence_after();
@@ -277,8 +328,8 @@ bool conv_halo_eligible(const sgb_conv_desc* d) {
 template <class T, int KIND, int BN>
 static int launch_halo(const sgb_conv_desc* d, const void* x, const void* w, void* y, cudaStream_t s) {
   constexpr int TC = 16 / sizeof(T);
-  constexpr int SA = 2;
-  constexpr int SB = BN == 256 ? 3 : (BN == 128 ? 4 : 6);
+  constexpr int SA = 4;
+  constexpr int SB = BN == 256 ? 3 : (BN == 128 ? 5 : 8);
   HaloParams p; p.d = *d; p.x = x; p.y = y; p.wpack = d->workspace;
   p.VR = d->out_h + d->kh - 1;
   p.HR = TILE_H + d->kh - 1; p.HC = TILE_W + d->kw - 1;
@@ -286,6 +337,8 @@ static int launch_halo(const sgb_conv_desc* d, const void* x, const void* w, voi
   p.left = d->transposed ? (d->kw - 1 - d->pad_x) : d->pad_x;
   p.row_tiles = (int)ceil_div((int64_t)d->n * p.VR, TILE_H);
   p.col_tiles = d->out_w / TILE_W;
+  p.ntiles = (d->co + BN - 1) / BN;
+  p.total_tiles = (int64_t)p.row_tiles * p.col_tiles * p.ntiles;
   p.taps = d->kh * d->kw;
   p.cblocks = (d->ci + 8 * TC - 1) / (8 * TC);
   int npix = p.HR * p.HC;
@@ -298,17 +351,16 @@ static int launch_halo(const sgb_conv_desc* d, const void* x, const void* w, voi
   SGB_REQUIRE(p.HR * p.HC * 8 <= 12 * 128, "patch too large");
   if (int r = pack_weights_umma(d, w, BN, s)) return r;
   const size_t smem = (size_t)SA * p.a_stage_bytes + (size_t)SB * BN * KB_BYTES_H + 1024;
+  SGB_REQUIRE(smem <= 226 * 1024, "shared memory budget exceeded");
   auto kern = conv_halo_kernel<T, KIND, BN, SA, SB>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     SGB_REQUIRE(e == cudaSuccess, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     attr_set = true;
   }
-  const int64_t gx = (int64_t)p.row_tiles * p.col_tiles;
-  const int ntiles = (d->co + BN - 1) / BN;
-  SGB_REQUIRE(gx <= 0x7fffffff && ntiles <= 65535, "problem too large for the halo conv grid");
-  kern<<<dim3((unsigned)gx, (unsigned)ntiles), 192, smem, s>>>(p);
+  const int64_t grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
+  kern<<<(unsigned)grid, HALO_THREADS, smem, s>>>(p);
   SGB_LAUNCH_CHECK();
   return 0;
 }

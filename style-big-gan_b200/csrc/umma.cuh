@@ -97,6 +97,14 @@ __device__ __forceinline__ uint32_t f32_to_tf32(float v) {
 
 
 
+// Ampere-style async copy, 16 bytes, L2 only; src_bytes = 0 zero-fills the destination (padding pixels)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
 // shared host helpers (conv_umma.cu)
 int pick_bn(int co);
 int elem_size(int dtype);
