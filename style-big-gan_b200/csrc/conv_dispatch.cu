@@ -11,6 +11,8 @@ bool conv_wgrad_umma_eligible(const sgb_conv_desc* d);
 bool conv_halo_eligible(const sgb_conv_desc* d);
 int conv_forward_halo(const sgb_conv_desc* d, const void* x, const void* w, void* y, cudaStream_t s);
 int conv_wgrad_umma(const sgb_conv_desc* d, const void* x, const void* dy, void* dw, cudaStream_t s);
+bool conv_wgrad_halo_eligible(const sgb_conv_desc* d);
+int conv_wgrad_halo(const sgb_conv_desc* d, const void* x, const void* dy, void* dw, cudaStream_t s);
 
 static int validate(const sgb_conv_desc* d) {
   SGB_REQUIRE(d != nullptr, "descriptor is NULL");
@@ -54,6 +56,9 @@ extern "C" int sgb_conv2d_wgrad(const sgb_conv_desc* d, const void* x, const voi
   SGB_REQUIRE(!d->transposed, "wgrad takes the non-transposed description (swap x and dy for conv_transpose2d)");
   SGB_REQUIRE(dw, "dw must not be NULL");
   SGB_REQUIRE((x && dy) || (int64_t)d->n == 0, "x and dy must not be NULL");
-  if (conv_wgrad_umma_eligible(d)) return conv_wgrad_umma(d, x, dy, dw, (cudaStream_t)stream);
+  if (conv_wgrad_umma_eligible(d)) {
+    if (conv_wgrad_halo_eligible(d)) return conv_wgrad_halo(d, x, dy, dw, (cudaStream_t)stream);
+    return conv_wgrad_umma(d, x, dy, dw, (cudaStream_t)stream);
+  }
   return conv_wgrad_simt(d, x, dy, dw, (cudaStream_t)stream);
 }

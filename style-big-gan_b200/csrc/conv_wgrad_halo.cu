@@ -1,0 +1,316 @@
+// tcgen05 weight-gradient kernel, "halo tile" form (channels_last, stride 1 or 2, 3x3 and 1x1 filters).
+//
+//   dW[o, c, ky, kx] = sum_{n, oy, ox} dy[n, oy, ox, o] * xs[n, oy*s + ky - pad, ox*s + kx - pad, c]
+//
+// A GEMM per filter tap whose K dimension is the output pixel: D_tap[o, c] = sum_p A[o, p] * B_tap[p, c] with
+// A = dy and B_tap = x shifted by the tap.  Both operands are "MN-major" for the tensor core (the channel is the
+// contiguous dimension in memory), so they are staged in the canonical no-swizzle MN-major layout
+//     [16-byte channel chunk j][pixel][16 B]          (SBO = plane stride between chunks, LBO = stride between
+//                                                      groups of 8 pixels)
+// conv_umma.cu's first wgrad kernel re-gathers x and dy once per tap (9x the traffic through LSU and L2).  Here a CTA
+// owns (128 output channels) x (BNC input channels) x (one filter ROW ky = kw taps) x (a range of pixel tiles):
+//   * a pixel tile is TH x 8 output pixels of one image (TH = 4 / 8 / 16 chosen by the launcher to fit >= 3 stages);
+//   * per tile the CTA stages the dy tile and ONE input patch (TH rows x (7*s + kw) columns) with cp.async (zero
+//     fill outside the image); the kw taps of the row are kw B descriptors into the same patch (start address moves
+//     by one pixel = 16 B), accumulating into kw TMEM accumulators of BNC columns;
+//   * stride 2: the patch columns are stored de-interleaved by parity, so that 8 consecutive output pixels of a row
+//     are still 16 B apart for every tap;
+//   * accumulators stay in TMEM across ALL tiles of the CTA; a single epilogue adds them to dW with
+//     red.global.add.f32 (dW zeroed by the launcher).
+// Warps 0-3: cp.async producers (+ optional in-place style scaling of the patch), then the epilogue.
+// Warp 4: MMA issuer (one lane), owns TMEM.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace sgb {
+
+constexpr int WG_THREADS = 160;
+constexpr int WG_LOOKAHEAD = 1;
+constexpr int NUM_PRODUCERS_WG = 128;          // tiles in flight per producer thread beyond the one being published
+
+struct WgradHaloParams {
+  sgb_conv_desc d;
+  const void* x; const void* dy; float* dw;
+  int TH;                     // tile rows; tile = TH x 8 output pixels
+  int row_tiles, col_tiles;   // per image
+  int64_t total_tiles;        // n * row_tiles * col_tiles
+  int64_t chunk_tiles;        // tiles per split
+  int ctiles;
+  int HC;                     // patch column slots per row = 7*s + kw
+  int QP;                     // slot offset of the odd-column plane (stride 2), 0 for stride 1
+  int a_plane, b_plane;       // bytes between channel chunks
+  int a_bytes, stage_bytes;
+  int stages;
+};
+
+template <class T, int KIND, int BNC>
+__global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_halo_kernel(WgradHaloParams p) {
+  constexpr int TC = 16 / sizeof(T);
+  constexpr int KPM = 32 / (int)sizeof(T);           // pixels per MMA (K = 32 bytes)
+  constexpr uint32_t IDESC = make_idesc(KIND, BNC, 1);
+  constexpr int MAX_STAGES = 4;
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], accum_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const sgb_conv_desc& d = p.d;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int otile = blockIdx.x;
+  const int ky = blockIdx.y / p.ctiles, ctile = blockIdx.y - ky * p.ctiles;
+  const int64_t t_begin = (int64_t)blockIdx.z * p.chunk_tiles;
+  const int64_t t_end = (t_begin + p.chunk_tiles < p.total_tiles) ? t_begin + p.chunk_tiles : p.total_tiles;
+  const int ntiles = t_end > t_begin ? (int)(t_end - t_begin) : 0;
+  const int SA = p.stages;
+  const int s = d.stride;
+  const int o0 = otile * UM, c0 = ctile * BNC;
+  const uint32_t tmem_cols = (d.kw * BNC <= 128) ? 128u : ((d.kw * BNC <= 256) ? 256u : 512u);
+
+  // channel chunks that are never written (beyond co / ci) must read as zero: clear the stages once
+  for (int i = threadIdx.x * 16; i < SA * p.stage_bytes; i += WG_THREADS * 16) *(uint4*)(smem + i) = make_uint4(0, 0, 0, 0);
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int i = 0; i < MAX_STAGES; i++) { mbar_init(smem_u32(&full_bar[i]), NUM_PRODUCERS_WG); mbar_init(smem_u32(&empty_bar[i]), 1); }
+      mbar_init(smem_u32(&accum_bar), 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(&tmem_base_slot), tmem_cols);
+  }
+  fence_proxy_async();          // the zero fill above is read by the tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp < 4) {
+    // =========================== producers ===========================
+    const int t = threadIdx.x;
+    const int cow = (d.co - o0 < UM) ? d.co - o0 : UM;             // valid channels of the dy tile (multiple of TC)
+    const int ciw = (d.ci - c0 < BNC) ? d.ci - c0 : BNC;           // valid channels of the x slice
+    const int cpa = cow / TC, cpb = ciw / TC;
+    int la = 0; while ((1 << la) < cpa) la++;                      // chunk lanes padded to a power of two (<= 32)
+    int lb = 0; while ((1 << lb) < cpb) lb++;
+    const int ja = t & ((1 << la) - 1), pa0 = t >> la, ppa = 128 >> la;   // chunk / first pixel / pixels per pass (dy tile)
+    const int jb = t & ((1 << lb) - 1), pb0 = t >> lb, ppb = 128 >> lb;   // same for the x patch
+    const int npa = p.TH * 8, npb = p.TH * p.HC;
+    const int ppb_div = ppb / p.HC, ppb_mod = ppb - ppb_div * p.HC;
+    const int pb0_r = pb0 / p.HC, pb0_c = pb0 - pb0_r * p.HC;
+    const T* xb = (const T*)p.x;
+    const T* dyb = (const T*)p.dy;
+    const float* scb = (const float*)d.in_scale;
+    const int tiles_per_img = p.row_tiles * p.col_tiles;
+    int pub = 0;
+
+    auto tile_origin = [&](int i, int& n, int& oy0, int& ox0) {
+      const int64_t tt = t_begin + i;
+      n = (int)(tt / tiles_per_img);
+      const int rem = (int)(tt - (int64_t)n * tiles_per_img);
+      const int tr = rem / p.col_tiles;
+      oy0 = tr * p.TH; ox0 = (rem - tr * p.col_tiles) * 8;
+    };
+
+    auto publish = [&](int i) {
+      const int sa = i % SA;
+      if (scb && jb < cpb) {                                        // in-place style scaling of the chunks this thread copied
+        int n, oy0, ox0;
+        tile_origin(i, n, oy0, ox0);
+        const float* sp = scb + (int64_t)n * d.ci + c0 + jb * TC;
+        float sv[TC];
+#pragma unroll
+        for (int e = 0; e < TC; e += 4) { const float4 q = __ldg((const float4*)(sp + e)); sv[e] = q.x; sv[e + 1] = q.y; sv[e + 2] = q.z; sv[e + 3] = q.w; }
+        uint8_t* bdst = smem + sa * p.stage_bytes + p.a_bytes + jb * p.b_plane;
+        int hr = pb0_r, hc = pb0_c;
+        for (int hp = pb0; hp < npb; hp += ppb) {
+          const int slot = (s == 1) ? hc : ((hc & 1) * p.QP + (hc >> 1));
+          uint4* q = (uint4*)(bdst + (hr * p.HC + slot) * 16);
+          uint4 v = *q;
+          if (KIND == 2) {
+            float* f = (float*)&v;
+#pragma unroll
+            for (int e = 0; e < 4; e++) f[e] *= sv[e % TC];
+          } else {
+            T* h = (T*)&v;
+#pragma unroll
+            for (int e = 0; e < TC; e++) h[e] = from_acc<T>(to_acc<T>(h[e]) * sv[e]);
+          }
+          *q = v;
+          hr += ppb_div; hc += ppb_mod;
+          if (hc >= p.HC) { hc -= p.HC; hr++; }
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(smem_u32(&full_bar[sa]));
+    };
+
+    for (int i = 0; i < ntiles; i++) {
+      const int sa = i % SA;
+      int n, oy0, ox0;
+      tile_origin(i, n, oy0, ox0);
+      mbar_wait(smem_u32(&empty_bar[sa]), ((i / SA) & 1) ^ 1);
+      const uint32_t a_dst = smem_u32(smem + sa * p.stage_bytes);
+      const uint32_t b_dst = a_dst + p.a_bytes;
+      // dy tile: pixel pp = ty * 8 + tx
+      if (ja < cpa) {
+        const T* src_n = dyb + (int64_t)n * d.y_strides[0] + o0 + ja * TC;
+        const uint32_t dst_j = a_dst + ja * p.a_plane;
+        for (int pp = pa0; pp < npa; pp += ppa) {
+          const int oy = oy0 + (pp >> 3), ox = ox0 + (pp & 7);
+          const bool ok = oy < d.out_h && ox < d.out_w;
+          const T* src = src_n + (int64_t)oy * d.y_strides[2] + (int64_t)ox * d.y_strides[3];
+          cp_async16(dst_j + pp * 16, ok ? (const void*)src : (const void*)dyb, ok ? 16u : 0u);
+        }
+      }
+      // x patch: row hr <-> input row (oy0 + hr) * s + ky - pad, column hc <-> input column ox0 * s - pad + hc
+      if (jb < cpb) {
+        const T* src_n = xb + (int64_t)n * d.x_strides[0] + c0 + jb * TC;
+        const uint32_t dst_j = b_dst + jb * p.b_plane;
+        const int ix0 = ox0 * s - d.pad_x;
+        int hr = pb0_r, hc = pb0_c;
+        for (int hp = pb0; hp < npb; hp += ppb) {
+          const int iy = (oy0 + hr) * s + ky - d.pad_y, ix = ix0 + hc;
+          const bool ok = iy >= 0 && iy < d.in_h && ix >= 0 && ix < d.in_w;
+          const int slot = (s == 1) ? hc : ((hc & 1) * p.QP + (hc >> 1));
+          const T* src = src_n + (int64_t)iy * d.x_strides[2] + (int64_t)ix * d.x_strides[3];
+          cp_async16(dst_j + (hr * p.HC + slot) * 16, ok ? (const void*)src : (const void*)xb, ok ? 16u : 0u);
+          hr += ppb_div; hc += ppb_mod;
+          if (hc >= p.HC) { hc -= p.HC; hr++; }
+        }
+      }
+      cp_async_commit();
+      if (i - pub >= WG_LOOKAHEAD) {
+        cp_async_wait<WG_LOOKAHEAD>();
+        publish(pub++);
+      }
+    }
+    cp_async_wait<0>();
+    while (pub < ntiles) publish(pub++);
+
+    // =========================== epilogue: lane = output channel, columns = (tap kx, input channel) ===========
+    if (ntiles > 0) {
+      mbar_wait(smem_u32(&accum_bar), 0);
+      tc_fence_after();
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+      const int o = o0 + threadIdx.x;
+      const int wy = d.flip ? d.kh - 1 - ky : ky;
+      for (int kx = 0; kx < d.kw; kx++) {
+        const int wx = d.flip ? d.kw - 1 - kx : kx;
+#pragma unroll 1
+        for (int cc = 0; cc < BNC; cc += 16) {
+          uint32_t acc[16];
+          tmem_ld16(lane_addr + kx * BNC + cc, acc);
+          if (o >= d.co) continue;
+#pragma unroll
+          for (int e = 0; e < 16; e++) {
+            const int c = c0 + cc + e;
+            if (c < d.ci) atomicAdd(p.dw + (((int64_t)o * d.ci + c) * d.kh + wy) * d.kw + wx, __uint_as_float(acc[e]));
+          }
+        }
+      }
+      tc_fence_before();
+    }
+  } else {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      const int mmas = p.TH * 8 / KPM;
+      const uint32_t b_lbo = (uint32_t)(p.HC * 16);             // next tile row = next patch row
+      for (int i = 0; i < ntiles; i++) {
+        const int sa = i % SA;
+        mbar_wait(smem_u32(&full_bar[sa]), (i / SA) & 1);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + sa * p.stage_bytes);
+        const uint32_t b_addr = a_addr + p.a_bytes;
+        for (int kx = 0; kx < d.kw; kx++) {
+          const uint32_t slot0 = (uint32_t)((kx % s) * p.QP + kx / s);
+          for (int kk = 0; kk < mmas; kk++) {
+            const int ty0 = kk * KPM / 8;
+            const uint64_t adesc = make_smem_desc(a_addr + (uint32_t)(kk * KPM * 16), 128, (uint32_t)p.a_plane);
+            const uint64_t bdesc = make_smem_desc(b_addr + (uint32_t)(ty0 * p.HC + slot0) * 16, b_lbo, (uint32_t)p.b_plane);
+            umma<KIND>(tmem_base + kx * BNC, adesc, bdesc, IDESC, (i > 0 || kk > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(smem_u32(&empty_bar[sa]));
+      }
+      if (ntiles > 0) umma_commit(smem_u32(&accum_bar));
+    }
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------
+bool conv_wgrad_halo_eligible(const sgb_conv_desc* d) {
+  if (!((d->kh == 3 && d->kw == 3) || (d->kh == 1 && d->kw == 1))) return false;
+  if (d->stride != 1 && d->stride != 2) return false;
+  if (d->force_simt == 2) return false;
+  return true;      // dtype / layout / alignment conditions are those of conv_wgrad_umma_eligible (checked by the caller)
+}
+
+template <class T, int KIND, int BNC>
+static int launch_wgrad_halo(const sgb_conv_desc* d, const void* x, const void* dy, float* dw, cudaStream_t st) {
+  constexpr int TC = 16 / sizeof(T);
+  WgradHaloParams p; p.d = *d; p.x = x; p.dy = dy; p.dw = dw;
+  const int s = d->stride;
+  p.HC = 7 * s + d->kw;
+  p.QP = (s == 1) ? 0 : (p.HC + 1) / 2;
+  p.ctiles = (d->ci + BNC - 1) / BNC;
+  const int otiles = (d->co + UM - 1) / UM;
+  const int budget = 224 * 1024;
+  int TH = 16, stages = 0;
+  for (;; TH >>= 1) {
+    int npa = TH * 8 + 1;
+    int npb = TH * p.HC; while (npb % 8 != 1) npb++;
+    p.a_plane = npa * 16; p.b_plane = npb * 16;
+    p.a_bytes = (UM / TC) * p.a_plane;
+    p.stage_bytes = (p.a_bytes + (BNC / TC) * p.b_plane + 127) / 128 * 128;
+    stages = budget / p.stage_bytes; if (stages > 4) stages = 4;
+    if (stages >= 3 || TH == 4) break;
+  }
+  SGB_REQUIRE(stages >= 2, "wgrad halo: tile does not fit shared memory");
+  p.TH = TH; p.stages = stages;
+  p.row_tiles = (d->out_h + TH - 1) / TH; p.col_tiles = (d->out_w + 7) / 8;
+  p.total_tiles = (int64_t)d->n * p.row_tiles * p.col_tiles;
+  const int64_t base = (int64_t)otiles * p.ctiles * d->kh;
+  int64_t splits = kNumSMs / base; if (splits < 1) splits = 1;
+  if (splits > p.total_tiles) splits = p.total_tiles;
+  p.chunk_tiles = ceil_div(p.total_tiles, splits);
+  splits = ceil_div(p.total_tiles, p.chunk_tiles);
+  SGB_REQUIRE((int64_t)p.ctiles * d->kh <= 65535 && splits <= 65535, "problem too large for the wgrad halo grid");
+  SGB_REQUIRE(aligned16(x) && aligned16(dy), "x and dy must be 16-byte aligned");
+  const size_t smem = (size_t)stages * p.stage_bytes + 1024;
+  auto kern = conv_wgrad_halo_kernel<T, KIND, BNC>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    SGB_REQUIRE(e == cudaSuccess, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    attr_set = true;
+  }
+  kern<<<dim3((unsigned)otiles, (unsigned)(p.ctiles * d->kh), (unsigned)splits), WG_THREADS, smem, st>>>(p);
+  SGB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <class T, int KIND>
+static int dispatch_wgrad_halo(const sgb_conv_desc* d, const void* x, const void* dy, float* dw, cudaStream_t s) {
+  if (d->ci <= 32) return launch_wgrad_halo<T, KIND, 32>(d, x, dy, dw, s);
+  if (d->ci <= 64) return launch_wgrad_halo<T, KIND, 64>(d, x, dy, dw, s);
+  return launch_wgrad_halo<T, KIND, 128>(d, x, dy, dw, s);
+}
+
+int conv_wgrad_halo(const sgb_conv_desc* d, const void* x, const void* dy, void* dw, cudaStream_t s) {
+  const int64_t wnum = (int64_t)d->co * d->ci * d->kh * d->kw;
+  cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * wnum, s);
+  SGB_REQUIRE(e == cudaSuccess, "memset failed");
+  if ((int64_t)d->n * d->out_h * d->out_w == 0) return 0;
+  if (d->dtype == SGB_F16) return dispatch_wgrad_halo<__half, 0>(d, x, dy, (float*)dw, s);
+  if (d->dtype == SGB_BF16) return dispatch_wgrad_halo<__nv_bfloat16, 1>(d, x, dy, (float*)dw, s);
+  return dispatch_wgrad_halo<float, 2>(d, x, dy, (float*)dw, s);
+}
+
+}  // namespace sgb

@@ -125,6 +125,12 @@ def test_umma_gradients_fp16():
     (1, 512, 512, 4, 3, 1, 1),        # several o / c tiles, 16 pixels only
     (4, 128, 8, 16, 1, 1, 0),         # 1x1, tiny co
     (2, 72, 264, 8, 3, 1, 1),         # co > 256 with a tail
+    (2, 64, 64, 40, 3, 1, 1),         # several row tiles per image, last one partial
+    (3, 128, 136, 20, 3, 1, 1),       # W = 20: partial column tile; two o tiles (136 = 128 + 8)
+    (2, 40, 64, 33, 3, 2, 0),         # stride 2, odd input (G up / D down weight gradients), ci tail
+    (2, 160, 32, 12, 3, 1, 1),        # two c tiles with a tail (160 = 128 + 32)
+    (2, 64, 128, 16, 1, 1, 0),        # 1x1 (D skip)
+    (70, 32, 32, 8, 3, 1, 1),         # more tiles than CTAs want: several tiles per CTA, pipeline wrap-around
 ])
 def test_umma_wgrad_vs_oracle(dtype, case):
     from sgb200.ops import conv2d_gradfix as cg
@@ -143,6 +149,13 @@ def test_umma_wgrad_vs_oracle(dtype, case):
         yo = torch.nn.functional.conv2d(xo, wo, stride=stride, padding=pad)
         dwo, = torch.autograd.grad(yo, [wo], dy.cpu().float())
         assert_close(dw, dwo, TOL, f'{case} {dtype} scale={scale is not None}')
+        # the per-tap kernel (first tensor-core wgrad) must agree with the halo-tile kernel
+        cg.use_halo_kernel = False
+        try:
+            dw1, = torch.autograd.grad(cg.conv2d(x, w, stride=stride, padding=pad, in_scale=scale), [w], dy)
+        finally:
+            cg.use_halo_kernel = True
+        assert_close(dw, dw1.float().cpu(), 3e-3, f'{case} {dtype} halo vs per-tap wgrad')
 
 
 @pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16, torch.float32])
