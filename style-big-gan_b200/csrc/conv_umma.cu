@@ -514,7 +514,7 @@ static int launch_umma(const sgb_conv_desc* d, const void* x, const void* w, voi
 
 template <class T, int KIND>
 static int dispatch_bn(const sgb_conv_desc* d, const void* x, const void* w, void* y, cudaStream_t s) {
-  switch (pick_bn(d->co)) {
+  switch (conv_bn(d)) {
     case 16:  return launch_umma<T, KIND, 16>(d, x, w, y, s);
     case 32:  return launch_umma<T, KIND, 32>(d, x, w, y, s);
     case 64:  return launch_umma<T, KIND, 64>(d, x, w, y, s);
@@ -601,7 +601,7 @@ extern "C" int64_t sgb_conv2d_workspace_bytes(const sgb_conv_desc* d) {
   if (d->dtype != SGB_F32 && d->dtype != SGB_F16 && d->dtype != SGB_BF16) return 0;
   const int es = sgb::elem_size(d->dtype);
   const int tc = 16 / es;
-  const int bn = sgb::pick_bn(d->co);
+  const int bn = sgb::conv_bn(d);
   const int64_t ntiles = (d->co + bn - 1) / bn, cblocks = (d->ci + 8 * tc - 1) / (8 * tc);
   return ntiles * d->kh * d->kw * cblocks * bn * sgb::KB_BYTES;
 }

@@ -287,7 +287,7 @@ static int launch_wgrad_halo(const sgb_conv_desc* d, const void* x, const void* 
   auto kern = conv_wgrad_halo_kernel<T, KIND, BNC>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     SGB_REQUIRE(e == cudaSuccess, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     attr_set = true;
   }

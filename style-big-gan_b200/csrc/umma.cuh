@@ -107,6 +107,8 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 // shared host helpers (conv_umma.cu)
 int pick_bn(int co);
+int conv_bn(const sgb_conv_desc* d);          // conv_halo.cu: output-channel tile for this descriptor
+int conv_halo_mode(const sgb_conv_desc* d);   // conv_halo.cu: 0 / 1 / 2 = halo-tile geometry, -1 = not eligible
 int elem_size(int dtype);
 int pack_weights_umma(const sgb_conv_desc* d, const void* w, int bn, cudaStream_t s);
 

@@ -160,22 +160,33 @@ def test_umma_wgrad_vs_oracle(dtype, case):
 
 @pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16, torch.float32])
 @pytest.mark.parametrize('case', [
-    # (N, Ci, Co, H, W, k, pad, transposed)   -- stride 1, W % 8 == 0 => halo-tile kernel
-    (1, 64, 64, 16, 16, 3, 1, False),
-    (3, 64, 64, 8, 8, 3, 1, False),           # tiles straddle images (virtual rows)
-    (2, 32, 48, 24, 16, 3, 1, False),         # H not a multiple of 16, co tail
-    (2, 136, 24, 16, 8, 3, 1, False),         # K tail (136 = 2*64 + 8)
-    (2, 128, 64, 16, 16, 3, 1, True),         # dgrad form
-    (2, 64, 64, 16, 16, 3, 0, True),          # transposed, pad 0 (output grows by 2)
-    (2, 64, 64, 18, 18, 3, 0, False),         # valid conv: out 16x16
-    (2, 64, 3, 16, 16, 1, 0, False),          # toRGB
-    (1, 512, 512, 8, 8, 3, 1, False),         # two N tiles
-    (1, 64, 272, 16, 16, 1, 0, False),
-    (5, 64, 64, 32, 32, 3, 1, False),
+    # (N, Ci, Co, H, W, k, pad, transposed, stride)   -- geometries of the halo-tile kernel
+    (1, 64, 64, 16, 16, 3, 1, False, 1),
+    (3, 64, 64, 8, 8, 3, 1, False, 1),           # tiles straddle images (virtual rows)
+    (2, 32, 48, 24, 16, 3, 1, False, 1),         # H not a multiple of 16, co tail
+    (2, 136, 24, 16, 8, 3, 1, False, 1),         # K tail (136 = 2*64 + 8)
+    (2, 128, 64, 16, 16, 3, 1, True, 1),         # dgrad form
+    (2, 64, 64, 16, 16, 3, 0, True, 1),          # transposed, pad 0 (output grows by 2)
+    (2, 64, 64, 18, 18, 3, 0, False, 1),         # valid conv: out 16x16
+    (2, 64, 3, 16, 16, 1, 0, False, 1),          # toRGB
+    (1, 512, 512, 8, 8, 3, 1, False, 1),         # two N tiles
+    (1, 64, 272, 16, 16, 1, 0, False, 1),
+    (5, 64, 64, 32, 32, 3, 1, False, 1),
+    (4, 512, 512, 4, 4, 3, 1, False, 1),         # W = 4: partial column tile
+    (2, 64, 64, 12, 20, 3, 1, False, 1),         # W = 20: partial last column tile
+    (2, 64, 128, 33, 33, 3, 0, False, 2),        # stride 2: D down path after the FIR (H+1 -> H/2)
+    (3, 40, 72, 17, 25, 3, 0, False, 2),         # stride 2, odd sizes, K tail (40 = 2*16 + 8), co tail
+    (2, 64, 64, 16, 16, 3, 1, False, 2),         # stride 2 with padding
+    (1, 24, 512, 9, 9, 3, 0, False, 2),          # stride 2, two N tiles
+    (2, 128, 64, 16, 16, 3, 0, True, 2),         # transposed stride 2: G up path (H -> 2H+1)
+    (3, 72, 40, 7, 11, 3, 0, True, 2),           # transposed stride 2, odd sizes, tails
+    (2, 64, 64, 16, 16, 3, 1, True, 2),          # transposed stride 2 with padding (H -> 2H-1)
+    (1, 64, 512, 8, 8, 3, 0, True, 2),           # transposed stride 2, co = 512 (four N tiles of 128)
+    (5, 32, 16, 40, 24, 3, 0, True, 2),          # several row tiles per image
 ])
 def test_halo_conv_vs_oracle_and_v1(dtype, case):
     from sgb200.ops import conv2d_gradfix as cg
-    n, ci, co, h, wd, k, pad, tr = case
+    n, ci, co, h, wd, k, pad, tr, stride = case
     torch.manual_seed(11)
     torch.backends.cudnn.allow_tf32 = True
     x = _cl(torch.randn(n, ci, h, wd).to(DEV, dtype))
@@ -185,14 +196,14 @@ def test_halo_conv_vs_oracle_and_v1(dtype, case):
     op = cg.conv_transpose2d if tr else cg.conv2d
     fo = torch.nn.functional.conv_transpose2d if tr else torch.nn.functional.conv2d
     for scale in ((None, s) if not tr else (None,)):
-        y = op(x, w, padding=pad, in_scale=scale)
+        y = op(x, w, stride=stride, padding=pad, in_scale=scale)
         xo = x.cpu().float() * (1 if scale is None else scale.cpu()[:, :, None, None])
-        yo = fo(xo, w.cpu().float(), padding=pad)
+        yo = fo(xo, w.cpu().float(), stride=stride, padding=pad)
         assert y.shape == yo.shape
         assert_close(y, yo, TOL, f'{case} {dtype} halo scale={scale is not None}')
         cg.use_halo_kernel = False
         try:
-            y1 = op(x, w, padding=pad, in_scale=scale)
+            y1 = op(x, w, stride=stride, padding=pad, in_scale=scale)
         finally:
             cg.use_halo_kernel = True
         assert_close(y, y1.float().cpu(), 2e-3 if dtype != torch.float32 else 1e-3, f'{case} {dtype} halo vs per-tap kernel')
