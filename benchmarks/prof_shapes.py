@@ -27,6 +27,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--cases', default='all')
     ap.add_argument('--reps', type=int, default=3)
+    ap.add_argument('--inner', type=int, default=1, help='back-to-back calls per timed region (amortises launch overhead)')
     args = ap.parse_args()
     torch.backends.cudnn.allow_tf32 = True
     f = upfirdn2d.setup_filter([1, 3, 3, 1]).to(DEV)
@@ -132,14 +133,15 @@ def main():
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            if name.startswith('wgrad'):
-                fn()
-            else:
-                with torch.no_grad():
+            for _ in range(args.inner):
+                if name.startswith('wgrad'):
                     fn()
+                else:
+                    with torch.no_grad():
+                        fn()
             e1.record()
             torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
+            ts.append(e0.elapsed_time(e1) / args.inner)
         ms = min(ts)
         msg = f'{name:28s} ms={ms:.4f}'
         if flops:

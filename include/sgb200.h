@@ -90,7 +90,8 @@ typedef struct {
   /* math mode and scratch */
   int32_t strict_fp32;    /* SGB_F32 only: 1 = fp32 FFMA arithmetic (1e-4 class); 0 = TF32 tensor cores allowed
                              (what torch.backends.cudnn.allow_tf32 means for the reference's cuDNN convs) */
-  int32_t force_simt;     /* A/B testing: 1 = never use the tensor-core kernels; 2 = tensor cores but not the halo-tile kernel */
+  int32_t force_simt;     /* A/B testing: 1 = never use the tensor-core kernels; 2 = tensor cores but not the halo-tile kernels */
+  int32_t halo_gt;        /* tuning / test knob: tiles per super-tile of the halo-tile kernel (1, 2, 4); 0 = automatic */
   void*   workspace;      /* caller-owned scratch of >= sgb_conv2d_workspace_bytes(d) bytes, 16-byte aligned, or
                              NULL (then only the SIMT kernels are used).  Holds the re-packed weights. */
   int64_t workspace_bytes;

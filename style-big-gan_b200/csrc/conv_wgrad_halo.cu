@@ -25,8 +25,8 @@
 namespace sgb {
 
 constexpr int WG_THREADS = 160;
-constexpr int WG_LOOKAHEAD = 1;
-constexpr int NUM_PRODUCERS_WG = 128;          // tiles in flight per producer thread beyond the one being published
+constexpr int WG_LOOKAHEAD = 1;          // tiles in flight per producer thread beyond the one being published
+constexpr int NUM_PRODUCERS_WG = 128;
 
 struct WgradHaloParams {
   sgb_conv_desc d;
@@ -143,11 +143,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_halo_kernel(WgradHal
       mbar_arrive(smem_u32(&full_bar[sa]));
     };
 
+    int sa_i = 0;
+    uint32_t ph_i = 0;
     for (int i = 0; i < ntiles; i++) {
-      const int sa = i % SA;
+      const int sa = sa_i;
       int n, oy0, ox0;
       tile_origin(i, n, oy0, ox0);
-      mbar_wait(smem_u32(&empty_bar[sa]), ((i / SA) & 1) ^ 1);
+      mbar_wait(smem_u32(&empty_bar[sa]), ph_i ^ 1);
+      if (++sa_i == SA) { sa_i = 0; ph_i ^= 1; }
       const uint32_t a_dst = smem_u32(smem + sa * p.stage_bytes);
       const uint32_t b_dst = a_dst + p.a_bytes;
       // dy tile: pixel pp = ty * 8 + tx
@@ -211,27 +214,34 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_halo_kernel(WgradHal
     }
   } else {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    // whole warp runs the loop (uniform values), lane 0 issues; descriptors as (lo, hi) halves, ring counters
+    {
       const int mmas = p.TH * 8 / KPM;
-      const uint32_t b_lbo = (uint32_t)(p.HC * 16);             // next tile row = next patch row
+      const uint32_t a_hi = smem_desc_hi((uint32_t)p.a_plane), b_hi = smem_desc_hi((uint32_t)p.b_plane);
+      const uint32_t a_lo_base = smem_desc_lo(smem_u32(smem), 128);
+      const uint32_t b_lo_base = smem_desc_lo(smem_u32(smem) + (uint32_t)p.a_bytes, (uint32_t)(p.HC * 16));   // LBO: next tile row = next patch row
+      const uint32_t stage_u = (uint32_t)p.stage_bytes >> 4;
+      const uint32_t b_row_u = (uint32_t)((KPM / 8) * p.HC);     // patch pixels between the first rows of consecutive MMAs
+      int sa = 0;
+      uint32_t pha = 0;
       for (int i = 0; i < ntiles; i++) {
-        const int sa = i % SA;
-        mbar_wait(smem_u32(&full_bar[sa]), (i / SA) & 1);
+        mbar_wait(smem_u32(&full_bar[sa]), pha);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + sa * p.stage_bytes);
-        const uint32_t b_addr = a_addr + p.a_bytes;
-        for (int kx = 0; kx < d.kw; kx++) {
-          const uint32_t slot0 = (uint32_t)((kx % s) * p.QP + kx / s);
-          for (int kk = 0; kk < mmas; kk++) {
-            const int ty0 = kk * KPM / 8;
-            const uint64_t adesc = make_smem_desc(a_addr + (uint32_t)(kk * KPM * 16), 128, (uint32_t)p.a_plane);
-            const uint64_t bdesc = make_smem_desc(b_addr + (uint32_t)(ty0 * p.HC + slot0) * 16, b_lbo, (uint32_t)p.b_plane);
-            umma<KIND>(tmem_base + kx * BNC, adesc, bdesc, IDESC, (i > 0 || kk > 0) ? 1u : 0u);
+        const uint32_t a_lo0 = a_lo_base + sa * stage_u, b_lo0 = b_lo_base + sa * stage_u;
+        if (lane == 0) {
+          for (int kx = 0; kx < d.kw; kx++) {
+            const uint32_t b_lo = b_lo0 + (uint32_t)((kx % s) * p.QP + kx / s);
+            const uint32_t tm = tmem_base + kx * BNC;
+#pragma unroll 4
+            for (int kk = 0; kk < mmas; kk++)
+              umma_lh<KIND>(tm, a_lo0 + kk * KPM, a_hi, b_lo + kk * b_row_u, b_hi, IDESC, (i > 0 || kk > 0) ? 1u : 0u);
           }
+          umma_commit(smem_u32(&empty_bar[sa]));
         }
-        umma_commit(smem_u32(&empty_bar[sa]));
+        __syncwarp();
+        if (++sa == SA) { sa = 0; pha ^= 1; }
       }
-      if (ntiles > 0) umma_commit(smem_u32(&accum_bar));
+      if (ntiles > 0 && lane == 0) umma_commit(smem_u32(&accum_bar));
     }
     __syncwarp();
   }

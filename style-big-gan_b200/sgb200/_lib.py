@@ -33,7 +33,7 @@ class ConvDesc(_c.Structure):
         ('x_strides', _I64x4), ('y_strides', _I64x4),
         ('in_scale', _vp), ('out_scale', _vp), ('noise', _vp), ('bias', _vp),
         ('act', _c.c_int32), ('alpha', _flt), ('gain', _flt), ('clamp', _flt),
-        ('strict_fp32', _c.c_int32), ('force_simt', _c.c_int32), ('workspace', _vp), ('workspace_bytes', _i64),
+        ('strict_fp32', _c.c_int32), ('force_simt', _c.c_int32), ('halo_gt', _c.c_int32), ('workspace', _vp), ('workspace_bytes', _i64),
     ]
 
 

@@ -19,7 +19,8 @@ from .. import _lib
 
 enabled = True                      # kept for API compatibility; the custom op is the only implementation
 use_tensor_cores = True             # False routes every convolution to the SIMT kernels (debugging / A-B tests)
-use_halo_kernel = True              # False keeps tensor cores but skips the halo-tile kernel (A-B tests)
+use_halo_kernel = True              # False keeps tensor cores but skips the halo-tile kernels (A-B tests)
+halo_gt = 0                         # tiles per super-tile of the halo-tile kernel: 0 = automatic, 1 / 2 / 4 forced (tests, tuning)
 weight_gradients_disabled = False   # forcefully disable computation of gradients with respect to the weights
 
 
@@ -72,6 +73,7 @@ def _make_desc(x, y, transposed, ci, co, kh, kw, stride, pad, groups, flip, in_s
     # (reference trainers.py:511 sets torch.backends.cudnn.allow_tf32 from perf.allow_tf32)
     d.strict_fp32 = 0 if torch.backends.cudnn.allow_tf32 else 1
     d.force_simt = (0 if use_halo_kernel else 2) if use_tensor_cores else 1
+    d.halo_gt = int(halo_gt)
     d.workspace, d.workspace_bytes = None, 0
     return d
 
