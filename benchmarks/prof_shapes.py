@@ -28,6 +28,7 @@ def main():
     ap.add_argument('--cases', default='all')
     ap.add_argument('--reps', type=int, default=3)
     ap.add_argument('--inner', type=int, default=1, help='back-to-back calls per timed region (amortises launch overhead)')
+    ap.add_argument('--graph', action='store_true', help='capture the inner calls in a CUDA graph and time its replay (device time only)')
     args = ap.parse_args()
     torch.backends.cudnn.allow_tf32 = True
     f = upfirdn2d.setup_filter([1, 3, 3, 1]).to(DEV)
@@ -129,16 +130,27 @@ def main():
         with torch.no_grad() if not name.startswith('wgrad') else torch.enable_grad():
             fn, flops, nbytes = cases[name]()
         ts = []
+        graph = None
+        if args.graph and not name.startswith('wgrad'):
+            with torch.no_grad():
+                fn()                                   # warm-up: attributes, allocator
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    for _ in range(args.inner):
+                        fn()
         for _ in range(args.reps):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for _ in range(args.inner):
+            for _ in range(args.inner if graph is None else 0):
                 if name.startswith('wgrad'):
                     fn()
                 else:
                     with torch.no_grad():
                         fn()
+            if graph is not None:
+                graph.replay()
             e1.record()
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1) / args.inner)

@@ -32,6 +32,7 @@
 //   warps 6-9  patch producers: cp.async 16-byte chunks global -> shared (zero-fill for padding), several patches in
 //              flight per thread, optional in-place style scaling, fence.proxy.async, mbarrier arrive
 #pragma once
+#include <cstdlib>
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -55,8 +56,10 @@ struct HaloParams {
   int lbo;              // bytes between channel chunks of the patch (padded)
   int a_stage_bytes;
   int sa, sb;           // stages
+  int tps;              // filter taps per weight stage (divides taps): one mbarrier round trip feeds tps * GT * 2 MMAs
   int stg_off;          // byte offset of the epilogue staging area
   int vec_store;
+  int debug;            // SGB_HALO_DEBUG bit mask (experiments only): 1 = no epilogue stores, 2 = no patch loads, 4 = no MMAs, 8 = no weight loads
   int tap_aoff[9];      // per tap: patch offset (pixels) of the A descriptor
   int tap_acc[9];       // per tap: accumulator (output phase) it feeds
 };
@@ -85,7 +88,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(HaloParams p
   constexpr int TC = 16 / sizeof(T);
   constexpr int CH = HALO_CH;
   constexpr int BK = CH * TC;
-  constexpr int B_STAGE_BYTES = BN * CH * 16;
+  constexpr int B_TAP_BYTES = BN * CH * 16;           // one tap's weight tile for one K stage
   constexpr int NPH = (MODE == 2) ? 4 : 1;            // output phases per tile
   constexpr int NACC = NPH * GT;                      // accumulators per super-tile
   static_assert(NACC * BN <= 512, "accumulators exceed TMEM");
@@ -134,7 +137,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(HaloParams p
     const int j = t & (CH - 1);                        // channel chunk owned by this thread
     const int pl = t / CH;
     const int npix = p.HR * p.HC;
-    const int lookahead = SA - 2;
+    const int lookahead = SA >= 3 ? SA - 2 : 1;
     const T* xb = (const T*)p.x;
     const float* scb = (const float*)d.in_scale;
     // per slot: patch coordinates (constant over tiles) and destination offset
@@ -204,7 +207,10 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(HaloParams p
       decode_tile(p, GT, tile, ntile, u0, x0);
       // per-slot source offsets (elements) of the patch pixels this thread stages; -1 = zero (padding / outside)
       int off[MAX_SLOTS];
-      {
+      if (p.debug & 32) {
+#pragma unroll
+        for (int i = 0; i < MAX_SLOTS; i++) off[i] = -1;
+      } else {
         const int n0 = u0 / p.VR, r0 = u0 - n0 * p.VR;             // MODE 1 / 2: tiles never straddle images
 #pragma unroll
         for (int i = 0; i < MAX_SLOTS; i++) {
@@ -238,7 +244,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(HaloParams p
         for (int i = 0; i < MAX_SLOTS; i++) {
           if (hrc[i] >= 0) {
             const bool ok = c_ok && off[i] >= 0;
-            cp_async16(dst + dsl[i], ok ? (const void*)(xb + off[i] + c) : (const void*)xb, ok ? 16u : 0u);
+            if (!(p.debug & 2)) cp_async16(dst + dsl[i], ok ? (const void*)(xb + off[i] + c) : (const void*)xb, ok ? 16u : 0u);
           }
         }
         cp_async_commit();
@@ -260,6 +266,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(HaloParams p
       const uint32_t a_lo_base = smem_desc_lo(smem_u32(a_base), (uint32_t)p.lbo);
       const uint32_t b_lo_base = smem_desc_lo(smem_u32(b_base), BN * 16);
       const uint32_t a_stage_u = (uint32_t)p.a_stage_bytes >> 4, kk_u = (uint32_t)(2 * p.lbo) >> 4;
+      const uint32_t b_stage_u = (uint32_t)(p.tps * B_TAP_BYTES) >> 4;
       int sa = 0, sb = 0, li = 0;
       uint32_t pha = 0, phb = 0;
       for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, li++) {
@@ -273,25 +280,30 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(HaloParams p
           mbar_wait(smem_u32(&a_full[sa]), pha);
           tc_fence_after();
           const uint32_t a_lo0 = a_lo_base + sa * a_stage_u;
-          for (int tap = 0; tap < p.taps; tap++) {
+          for (int tap0 = 0; tap0 < p.taps; tap0 += p.tps) {
             mbar_wait(smem_u32(&b_full[sb]), phb);
             tc_fence_after();
-            const int acc = (MODE == 2) ? p.tap_acc[tap] : 0;
-            const uint32_t a_lo = a_lo0 + (uint32_t)p.tap_aoff[tap];
-            const uint32_t b_lo = b_lo_base + sb * (B_STAGE_BYTES >> 4);
-            const uint32_t first = (started >> acc) & 1u;
+            const uint32_t b_lo0 = b_lo_base + sb * b_stage_u;
             if (lane == 0) {
+              for (int t = 0; t < p.tps; t++) {
+                const int tap = tap0 + t;
+                const int acc = (MODE == 2) ? p.tap_acc[tap] : 0;
+                const uint32_t a_lo = a_lo0 + (uint32_t)p.tap_aoff[tap];
+                const uint32_t b_lo = b_lo0 + t * (B_TAP_BYTES >> 4);
+                const uint32_t first = (started >> acc) & 1u;
 #pragma unroll
-              for (int g = 0; g < GT; g++) {
+                for (int g = 0; g < GT; g++) {
+                  if (p.debug & 4) break;
 #pragma unroll
-                for (int kk = 0; kk < CH / 2; kk++)
-                  umma_lh<KIND>(tmem_d + (g * NPH + acc) * BN, a_lo + g * TILE_W + kk * kk_u, a_hi, b_lo + kk * (2 * BN), b_hi, IDESC,
-                                first | (uint32_t)kk);
+                  for (int kk = 0; kk < CH / 2; kk++)
+                    umma_lh<KIND>(tmem_d + (g * NPH + acc) * BN, a_lo + g * TILE_W + kk * kk_u, a_hi, b_lo + kk * (2 * BN), b_hi, IDESC,
+                                  first | (uint32_t)kk);
+                }
+                started |= 1u << acc;
               }
               umma_commit(smem_u32(&b_empty[sb]));
             }
             __syncwarp();
-            started |= 1u << acc;
             if (++sb == SB) { sb = 0; phb ^= 1; }
           }
           if (lane == 0) umma_commit(smem_u32(&a_empty[sa]));
@@ -314,12 +326,18 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(HaloParams p
         const int ntile = (int)(tile % p.ntiles);
         const uint8_t* wsrc = (const uint8_t*)p.wpack + (int64_t)ntile * p.taps * cb128 * (BN * 128);
         for (int cb = 0; cb < p.cblocks; cb++) {
-          const uint8_t* wcb = wsrc + (int64_t)(cb / HALVES) * (BN * 128) + (cb % HALVES) * B_STAGE_BYTES;
-          for (int tap = 0; tap < p.taps; tap++) {
+          const uint8_t* wcb = wsrc + (int64_t)(cb / HALVES) * (BN * 128) + (cb % HALVES) * B_TAP_BYTES;
+          for (int tap0 = 0; tap0 < p.taps; tap0 += p.tps) {
             mbar_wait(smem_u32(&b_empty[sb]), phb ^ 1);
             const uint32_t bar = smem_u32(&b_full[sb]);
-            mbar_arrive_expect_tx(bar, B_STAGE_BYTES);
-            bulk_copy_g2s(smem_u32(b_base + sb * B_STAGE_BYTES), wcb + (int64_t)tap * cb128 * (BN * 128), B_STAGE_BYTES, bar);
+            if (p.debug & 8) {
+              mbar_arrive(bar);
+            } else {
+              mbar_arrive_expect_tx(bar, p.tps * B_TAP_BYTES);
+              const uint32_t dst = smem_u32(b_base + sb * (p.tps * B_TAP_BYTES));
+              for (int t = 0; t < p.tps; t++)
+                bulk_copy_g2s(dst + t * B_TAP_BYTES, wcb + (int64_t)(tap0 + t) * cb128 * (BN * 128), B_TAP_BYTES, bar);
+            }
             if (++sb == SB) { sb = 0; phb ^= 1; }
           }
         }
@@ -346,6 +364,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(HaloParams p
       tc_fence_after();
 #pragma unroll 1
       for (int a = 0; a < NACC; a++) {
+        if (p.debug & 16) break;
         const int g = a / NPH, ph = a - g * NPH;
         const int py = ph >> 1, px = ph & 1;
         // output pixel of tile row mm (this thread's own row for the maths, other rows in the store phase)
@@ -421,7 +440,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(HaloParams p
             if (o < d.co) {
 #pragma unroll
               for (int k = 0; k < NQ; k++) {
-                if (yoff[k] >= 0) {
+                if (yoff[k] >= 0 && !(p.debug & 1)) {
                   const uint4 v = *(const uint4*)(stg + (q_pix + PPI * k) * PITCH + q_chunk * 16);
                   *(uint4*)((T*)p.y + yoff[k] + o) = v;
                 }
@@ -503,19 +522,31 @@ int launch_halo(const sgb_conv_desc* d, const void* x, const void* w, void* y, c
   SGB_REQUIRE(aligned16(x) && aligned16(d->workspace), "x and workspace must be 16-byte aligned");
   SGB_REQUIRE(d->act == 0 || d->act == SGB_ACT_LINEAR || d->act == SGB_ACT_LRELU, "fused epilogue supports linear and lrelu only");
   if (d->act == SGB_ACT_LINEAR) p.d.alpha = 1.f;
+  static const int dbg = [] { const char* e = getenv("SGB_HALO_DEBUG"); return e ? atoi(e) : 0; }();
+  p.debug = dbg;
   if (int r = pack_weights_umma(d, w, BN, s)) return r;
-  // shared-memory plan: staging slabs, then as many patch stages as useful, the rest for weight stages
+  // shared-memory plan: staging slabs; weight stages of `tps` taps (largest divisor of taps that leaves room: fewer
+  // mbarrier round trips per MMA) with enough bytes in flight to cover the L2 latency; the rest for patch stages
   const int budget = 225 * 1024;
   const int stg_bytes = 4 * 32 * PITCH;
-  const int b_stage = BN * CH * 16;
-  int sa = MAX_SA, sb;
-  for (;; sa--) {
-    sb = (budget - stg_bytes - sa * p.a_stage_bytes) / b_stage;
-    if (sb >= (sa > 3 ? 6 : 2) || sa == 3) break;
+  const int b_tap = BN * CH * 16;
+  int sa = 0, sb = 0, tps = 1;
+  for (int cand = p.taps; cand >= 1; cand--) {
+    if (p.taps % cand) continue;
+    const int b_stage_c = cand * b_tap;
+    int sb_c = (64 * 1024 + b_stage_c - 1) / b_stage_c;              // >= 64 KB of weights in flight ...
+    if (sb_c < 2) sb_c = 2;                                          // ... and at least double buffering
+    if (sb_c > MAX_SB) sb_c = MAX_SB;
+    const int sa_c = (budget - stg_bytes - sb_c * b_stage_c) / p.a_stage_bytes;
+    if (sa_c >= 3 || cand == 1) { tps = cand; sb = sb_c; sa = sa_c > MAX_SA ? MAX_SA : sa_c; break; }
   }
-  if (sb > MAX_SB) sb = MAX_SB;
-  SGB_REQUIRE(sb >= 2, "shared memory budget exceeded");
-  p.sa = sa; p.sb = sb;
+  SGB_REQUIRE(sa >= 2 && sb >= 2, "shared memory budget exceeded");
+  const int b_stage = tps * b_tap;
+  {                                                                  // left-over space: more weight stages
+    const int extra = (budget - stg_bytes - sa * p.a_stage_bytes - sb * b_stage) / b_stage;
+    sb = (sb + extra > MAX_SB) ? MAX_SB : sb + extra;
+  }
+  p.sa = sa; p.sb = sb; p.tps = tps;
   p.stg_off = sa * p.a_stage_bytes + sb * b_stage;
   const size_t smem = (size_t)p.stg_off + stg_bytes + 1024;
   auto kern = conv_halo_kernel<T, KIND, BN, MODE, GT>;
