@@ -90,6 +90,38 @@ def _attach_workspace(d, device):
     return ws
 
 
+def _tc_multiple(x, groups):
+    """Channel multiple (one 16-byte vector) the tensor-core kernels need, or 0 when they will not be used."""
+    if not use_tensor_cores or groups != 1:
+        return 0
+    if x.dtype in (torch.float16, torch.bfloat16):
+        return 8
+    if x.dtype == torch.float32 and torch.backends.cudnn.allow_tf32:
+        return 4
+    return 0
+
+
+def _pad_channels(t, mult):
+    """[N,C,H,W] -> channels_last copy with C padded with zeros to a multiple of `mult` (RGB tensors, the
+    minibatch-stddev channel): makes the convolution eligible for the tensor-core kernels."""
+    n, c, h, w = t.shape
+    cp = (-c) % mult
+    out = torch.empty([n, c + cp, h, w], dtype=t.dtype, device=t.device, memory_format=torch.channels_last)
+    out[:, :c].copy_(t)
+    if cp:
+        out[:, c:].zero_()
+    return out
+
+
+def _pad_dim(t, dim, mult):
+    cp = (-t.shape[dim]) % mult
+    if cp == 0:
+        return t
+    shape = list(t.shape)
+    shape[dim] = cp
+    return torch.cat([t, t.new_zeros(shape)], dim=dim)
+
+
 def _scale_arg(in_scale, x):
     if in_scale is None:
         return None
@@ -151,12 +183,19 @@ def _conv2d_op(transpose, weight_shape, stride, padding, output_padding, dilatio
             oh, ow = out_hw(input.shape[2], input.shape[3])
             if oh < 1 or ow < 1:
                 raise RuntimeError('conv: output would be empty')
-            y = torch.empty([input.shape[0], co, oh, ow], dtype=input.dtype, device=input.device,
-                            memory_format=_lib.out_format(input))
             sc = _scale_arg(in_scale, input)
+            x_, ci_, fmt = input, ci, _lib.out_format(input)
+            mult = _tc_multiple(input, groups)
+            if mult and ci % mult != 0 and input.numel() > 0:
+                # few / odd input channels (RGB, minibatch-stddev): zero-pad them to one 16-byte vector
+                x_ = _pad_channels(input, mult)
+                w = _pad_dim(w, 0 if transpose else 1, mult)
+                sc = _pad_dim(sc, 1, mult) if sc is not None else None
+                ci_, fmt = x_.shape[1], torch.channels_last
+            y = torch.empty([input.shape[0], co, oh, ow], dtype=input.dtype, device=input.device, memory_format=fmt)
             b = bias.contiguous() if bias is not None else None
             if y.numel() > 0:
-                d = _make_desc(input, y, transpose, ci, co, kh, kw, s, padding, groups, flip, sc, b)
+                d = _make_desc(x_, y, transpose, ci_, co, kh, kw, s, padding, groups, flip, sc, b)
                 # algorithmic work: non-zero MACs only for the transposed form
                 px = (input.shape[2] * input.shape[3]) if transpose else (oh * ow)
                 flops = 2.0 * input.shape[0] * px * (co // groups) * ci * kh * kw
@@ -164,7 +203,7 @@ def _conv2d_op(transpose, weight_shape, stride, padding, output_padding, dilatio
                 ws = _attach_workspace(d, input.device)
                 tc = _lib.lib().sgb_conv2d_uses_tensor_cores(d)
                 with torch.cuda.device(input.device), _lib.prof('conv_fwd_tc' if tc else 'conv_fwd_simt', flops, nbytes):
-                    rc = _lib.lib().sgb_conv2d_forward(d, _lib.ptr(input), _lib.ptr(w), _lib.ptr(y), _lib.stream_ptr(input.device))
+                    rc = _lib.lib().sgb_conv2d_forward(d, _lib.ptr(x_), _lib.ptr(w), _lib.ptr(y), _lib.stream_ptr(input.device))
                 _lib.check(rc, 'conv2d_forward')
             ctx.save_for_backward(input, weight, in_scale)
             ctx.has_bias = bias is not None
@@ -210,12 +249,33 @@ def _conv2d_op(transpose, weight_shape, stride, padding, output_padding, dilatio
                     raise NotImplementedError('in_scale with conv_transpose2d weight gradients: scale the input explicitly')
                 x_, dy_ = grad_output, input
                 d = _make_desc(x_, dy_, False, co, ci, kh, kw, s, padding, groups, flip)
-            dw = torch.empty(weight_shape, dtype=_lib.acc_dtype(input.dtype), device=input.device)
             flops = 2.0 * dy_.shape[0] * dy_.shape[2] * dy_.shape[3] * dy_.shape[1] * (x_.shape[1] // groups) * kh * kw
-            nbytes = (x_.numel() + dy_.numel()) * x_.element_size() + dw.numel() * dw.element_size()
+            nbytes = (x_.numel() + dy_.numel()) * x_.element_size()
+            # dw has the layout of the weight of the NON-transposed conv x_ -> dy_: [C(dy_), C(x_)/groups, kh, kw]
+            mult = _tc_multiple(input, groups)
+            cx, cy = x_.shape[1], dy_.shape[1]
+            padded = bool(mult) and (cx % mult != 0 or cy % mult != 0) and x_.numel() > 0 and dy_.numel() > 0
+            if padded:      # few / odd channels: zero-pad to one 16-byte vector so the tensor-core kernel applies
+                if cx % mult != 0:
+                    x_ = _pad_channels(x_, mult)
+                    if d.in_scale:
+                        sc = _pad_dim(sc, 1, mult)
+                if cy % mult != 0:
+                    dy_ = _pad_channels(dy_, mult)
+                x_ = x_.contiguous(memory_format=torch.channels_last)
+                dy_ = dy_.contiguous(memory_format=torch.channels_last)
+                d = _make_desc(x_, dy_, False, x_.shape[1], dy_.shape[1], kh, kw, s, padding, groups, flip,
+                               sc if d.in_scale else None)
+            dwf = torch.empty([dy_.shape[1], x_.shape[1] // groups, kh, kw], dtype=_lib.acc_dtype(input.dtype), device=input.device)
+            nbytes += dwf.numel() * dwf.element_size()
             with torch.cuda.device(input.device), _lib.prof('conv_wgrad', flops, nbytes):
-                rc = _lib.lib().sgb_conv2d_wgrad(d, _lib.ptr(x_), _lib.ptr(dy_), _lib.ptr(dw), _lib.stream_ptr(input.device))
+                rc = _lib.lib().sgb_conv2d_wgrad(d, _lib.ptr(x_), _lib.ptr(dy_), _lib.ptr(dwf), _lib.stream_ptr(input.device))
             _lib.check(rc, 'conv2d_wgrad')
+            if padded:
+                dwf = dwf[:cy, :cx // groups]
+            # the non-transposed layout [C(dy_), C(x_), kh, kw] is the op's weight layout in both cases:
+            # conv2d: [co, ci]; conv_transpose2d (x_ = grad_output, dy_ = input): [ci, co]
+            dw = dwf.reshape(weight_shape) if not padded else dwf.contiguous().reshape(weight_shape)
             ctx.save_for_backward(grad_output, input, in_scale)
             return dw.to(input.dtype)
 

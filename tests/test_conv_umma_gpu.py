@@ -213,3 +213,41 @@ def test_halo_conv_vs_oracle_and_v1(dtype, case):
             cg.use_halo_kernel = True
         assert_close(y, y1.float().cpu(), {torch.float32: 1e-3, torch.float16: 2e-3, torch.bfloat16: 8e-3}[dtype],
                      f'{case} {dtype} halo vs per-tap kernel')
+
+
+@pytest.mark.parametrize('dtype', [torch.float16, torch.float32])
+@pytest.mark.parametrize('case', [
+    # (N, Ci, Co, H, k, pad, nchw_input)
+    (4, 3, 64, 32, 1, 0, True),        # fromRGB: NCHW image in, channels_last features out
+    (4, 3, 64, 32, 1, 0, False),
+    (4, 64, 3, 32, 1, 0, False),       # toRGB
+    (8, 513, 512, 4, 3, 1, False),     # D epilogue conv after the minibatch-stddev channel
+    (2, 5, 7, 9, 3, 1, False),         # both channel counts odd
+])
+def test_channel_padding_makes_small_channel_convs_tensor_core(dtype, case):
+    """Convolutions whose channel count is not a multiple of one 16-byte vector are zero-padded in the op so that
+    forward, data gradient and weight gradient all run on the tensor-core kernels; results vs the CPU oracle."""
+    from sgb200.ops import conv2d_gradfix as cg
+    from sgb200 import _lib
+    n, ci, co, h, k, pad, nchw = case
+    torch.manual_seed(21)
+    torch.backends.cudnn.allow_tf32 = True
+    x = torch.randn(n, ci, h, h).to(DEV, dtype)
+    if not nchw:
+        x = _cl(x)
+    x.requires_grad_(True)
+    w = (torch.randn(co, ci, k, k) / math.sqrt(ci * k * k)).to(DEV, dtype).requires_grad_(True)
+    _lib.profile_start()
+    y = cg.conv2d(x, w, padding=pad)
+    dy = _cl(torch.randn(y.shape).to(DEV, dtype))        # gradients arrive channels_last in the networks
+    dx, dw = torch.autograd.grad(y, [x, w], dy)
+    torch.cuda.synchronize()
+    kinds = set(_lib.profile_stop().summary())
+    assert 'conv_fwd_simt' not in kinds, kinds          # forward and dgrad both on tensor cores
+    xo = x.detach().cpu().float().requires_grad_(True)
+    wo = w.detach().cpu().float().requires_grad_(True)
+    yo = torch.nn.functional.conv2d(xo, wo, padding=pad)
+    dxo, dwo = torch.autograd.grad(yo, [xo, wo], dy.cpu().float())
+    assert_close(y, yo, TOL, f'{case} {dtype} y')
+    assert_close(dx, dxo, TOL, f'{case} {dtype} dx')
+    assert_close(dw, dwo, TOL, f'{case} {dtype} dw')
