@@ -166,6 +166,7 @@ def main():
     ap.add_argument('--fp32-mode', default='tf32', choices=['tf32', 'strict'],
                     help="arithmetic of fp32 convolutions: 'tf32' = TF32 tensor cores (torch.backends.cudnn.allow_tf32=True, "
                          "1e-2 class), 'strict' = fp32 FFMA (the reference default perf.allow_tf32=False, 1e-4 class)")
+    ap.add_argument('--no-graphs', action='store_true', help='launch every kernel eagerly instead of replaying per-phase CUDA graphs')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--breakdown', default=None, help='write the per-kernel-family time table (json) here')
@@ -191,7 +192,7 @@ def main():
     torch.backends.cudnn.benchmark = False
     torch.backends.cudnn.allow_tf32 = (args.fp32_mode == 'tf32')
     torch.backends.cuda.matmul.allow_tf32 = (args.fp32_mode == 'tf32')
-    cfg = workload_config(args.workload)
+    cfg = workload_config(args.workload, cuda_graphs=not args.no_graphs)
     tr = training.Trainer(cfg, device, rank=rank, world_size=world)
     R, N = cfg.img_resolution, cfg.batch_gpu
     host_real = torch.randint(0, 256, [N, cfg.img_channels, R, R], dtype=torch.uint8).pin_memory()
@@ -208,19 +209,19 @@ def main():
         barrier()
         if profile:
             _lib.profile_start()
-        n0 = _lib.launch_count()
+        n0 = _lib.launch_count() + tr.replayed_launches
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         last = None
         for _ in range(steps):
             real = host_real.to(device, non_blocking=True) if from_host else dev_real
-            out = tr.iteration(real)
+            out = tr.iteration(real, eager=profile)      # per-launch events need eager launches
             if from_host:
                 last = {k: float(v) for k, v in out.items()}      # D2H read of every loss of the step
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
-        launches = _lib.launch_count() - n0
+        launches = _lib.launch_count() + tr.replayed_launches - n0
         summ = _lib.profile_stop().summary() if profile else None
         if world > 1:
             t = torch.tensor([ms], device=device, dtype=torch.float64)
@@ -236,8 +237,11 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    ms, launches, summ, _ = timed_loop(args.steps, from_host=False, profile=True)
+    ms, launches, _, _ = timed_loop(args.steps, from_host=False, profile=False)
     clocks = sampler.stop() if sampler else None
+    # per-kernel-family device time (roofline leg): the same K steps launched eagerly with CUDA events around
+    # every libsgb200 launch; not part of the reported step time
+    _, _, summ, _ = timed_loop(args.steps, from_host=False, profile=True)
 
     e2e = None
     if not args.no_e2e:
@@ -286,6 +290,7 @@ def main():
                 config=dict(workload=WORKLOAD_DESC[args.workload], batch_per_gpu=N, global_batch=N * world, resolution=R,
                             parallelism=f'dp{world}', g_reg_interval=cfg.g_reg_interval, d_reg_interval=cfg.d_reg_interval,
                             layout='channels_last' if cfg.channels_last else 'nchw', fp32_mode=args.fp32_mode,
+                            launch='eager' if args.no_graphs else 'cuda graphs (one per training phase)',
                             l2='working set per step (activations, GBs) far exceeds the 126 MB L2; no explicit flush'),
                 gpu_launches=int(launches), e2e=e2e, roofline=roof, cpu_baseline=cpu, clocks=clocks)
     print(json.dumps(line), flush=True)

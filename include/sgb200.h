@@ -110,6 +110,8 @@ int sgb_conv2d_wgrad(const sgb_conv_desc* d, const void* x, const void* dy, void
 /* 1 if the tcgen05 (tensor-core) implicit-GEMM path will be used for this descriptor, 0 if the
  * generic SIMT kernel; for reporting only. */
 int sgb_conv2d_uses_tensor_cores(const sgb_conv_desc* d);
+/* same question for sgb_conv2d_wgrad */
+int sgb_conv2d_wgrad_uses_tensor_cores(const sgb_conv_desc* d);
 
 /* ---- modulation helpers (activation-sized passes of modulated_conv2d, generators.py:80-87; fma.py) ----
  * y[n,c,h,w] = x[n,c,h,w] * s[n,c] (+ t[n,h,w] if t != NULL).  s, t accumulator-typed, dense. */

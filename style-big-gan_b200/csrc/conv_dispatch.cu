@@ -35,6 +35,18 @@ static int validate(const sgb_conv_desc* d) {
 
 using namespace sgb;
 
+// 2 = halo-tile tensor-core kernel, 1 = per-tap tensor-core kernel (16-bit types only: kind::tf32 does not take the
+// MN-major operands the weight gradient needs; fp32 runs the 3 x bf16 split inside the halo kernel), 0 = SIMT
+static int wgrad_route(const sgb_conv_desc* d) {
+  if (!conv_wgrad_umma_eligible(d)) return 0;
+  if (conv_wgrad_halo_eligible(d)) return 2;
+  return d->dtype == SGB_F32 ? 0 : 1;
+}
+
+extern "C" int sgb_conv2d_wgrad_uses_tensor_cores(const sgb_conv_desc* d) {
+  return (d && !d->transposed && wgrad_route(d) != 0) ? 1 : 0;
+}
+
 extern "C" int sgb_conv2d_uses_tensor_cores(const sgb_conv_desc* d) {
   return (d && conv_umma_eligible(d)) ? 1 : 0;
 }
@@ -56,9 +68,10 @@ extern "C" int sgb_conv2d_wgrad(const sgb_conv_desc* d, const void* x, const voi
   SGB_REQUIRE(!d->transposed, "wgrad takes the non-transposed description (swap x and dy for conv_transpose2d)");
   SGB_REQUIRE(dw, "dw must not be NULL");
   SGB_REQUIRE((x && dy) || (int64_t)d->n == 0, "x and dy must not be NULL");
-  if (conv_wgrad_umma_eligible(d)) {
-    if (conv_wgrad_halo_eligible(d)) return conv_wgrad_halo(d, x, dy, dw, (cudaStream_t)stream);
-    return conv_wgrad_umma(d, x, dy, dw, (cudaStream_t)stream);
+  switch (wgrad_route(d)) {
+    case 2: return conv_wgrad_halo(d, x, dy, dw, (cudaStream_t)stream);
+    case 1: return conv_wgrad_umma(d, x, dy, dw, (cudaStream_t)stream);
+    default: break;
   }
   return conv_wgrad_simt(d, x, dy, dw, (cudaStream_t)stream);
 }

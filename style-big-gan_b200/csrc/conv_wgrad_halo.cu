@@ -254,6 +254,255 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_halo_kernel(WgradHal
   }
 }
 
+// ---- fp32 tensors: 3 x bf16 split ----------------------------------------------------------------------------------
+// tcgen05 takes MN-major (channel-contiguous) operands for the 16-bit kinds only in the no-swizzle layout used here:
+// kind::tf32 with MN-major operands returns zeros (measured; the old per-tap kernel had the same defect).  fp32
+// gradients / activations are therefore split into two bf16 terms each, v = hi + lo, and
+//     dW  ~=  dy_hi * x_hi  +  dy_hi * x_lo  +  dy_lo * x_hi          (error ~2^-16 relative: better than TF32's 2^-11)
+// is accumulated in fp32 by three kind::f16 MMAs per K step.  Data flow per tile:
+//   cp.async  fp32 chunks  ->  STAGING buffer (thread-private positions, WG_LOOKAHEAD + 1 buffers, no barriers)
+//   the same thread: LDS its two fp32 chunks of an 8-channel group, (x: multiply by the style), split, STS the bf16
+//   hi / lo chunks into the MMA stage ([hi planes | lo planes] x [chunk of 8 channels][pixel][16 B]), fence, arrive.
+template <int BNC>
+__global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_split_kernel(WgradHaloParams p) {
+  constexpr int KPM = 16;                            // pixels per MMA (bf16: K = 32 bytes)
+  constexpr uint32_t IDESC = make_idesc(1, BNC, 1);  // bf16 operands, both MN-major
+  constexpr int MAX_STAGES = 4;
+  constexpr int NSTG = WG_LOOKAHEAD + 1;
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], accum_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const sgb_conv_desc& d = p.d;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int otile = blockIdx.x;
+  const int ky = blockIdx.y / p.ctiles, ctile = blockIdx.y - ky * p.ctiles;
+  const int64_t t_begin = (int64_t)blockIdx.z * p.chunk_tiles;
+  const int64_t t_end = (t_begin + p.chunk_tiles < p.total_tiles) ? t_begin + p.chunk_tiles : p.total_tiles;
+  const int ntiles = t_end > t_begin ? (int)(t_end - t_begin) : 0;
+  const int SA = p.stages;
+  const int s = d.stride;
+  const int o0 = otile * UM, c0 = ctile * BNC;
+  const uint32_t tmem_cols = (d.kw * BNC <= 128) ? 128u : ((d.kw * BNC <= 256) ? 256u : 512u);
+  // staging: fp32 layout [chunk of 4 channels][pixel][16 B] with the same plane strides (32 + BNC/4 planes);
+  // MMA stage: [A hi: 16 planes][A lo: 16][B hi: BNC/8][B lo: BNC/8], plane = (pixels padded) * 16 B
+  uint8_t* stg_base = smem;
+  uint8_t* mma_base = smem + NSTG * p.stage_bytes;
+  const int a_half = 16 * p.a_plane, b_half = (BNC / 8) * p.b_plane;
+
+  for (int i = threadIdx.x * 16; i < (NSTG + SA) * p.stage_bytes; i += WG_THREADS * 16) *(uint4*)(smem + i) = make_uint4(0, 0, 0, 0);
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int i = 0; i < MAX_STAGES; i++) { mbar_init(smem_u32(&full_bar[i]), NUM_PRODUCERS_WG); mbar_init(smem_u32(&empty_bar[i]), 1); }
+      mbar_init(smem_u32(&accum_bar), 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(&tmem_base_slot), tmem_cols);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp < 4) {
+    // =========================== producers / converters ===========================
+    const int t = threadIdx.x;
+    const int cow = (d.co - o0 < UM) ? d.co - o0 : UM;             // valid channels (multiples of 4)
+    const int ciw = (d.ci - c0 < BNC) ? d.ci - c0 : BNC;
+    const int ga = (cow + 7) / 8, gb = (ciw + 7) / 8;              // 8-channel groups: one thread item = 2 fp32 chunks
+    int la = 0; while ((1 << la) < ga) la++;
+    int lb = 0; while ((1 << lb) < gb) lb++;
+    const int ja = t & ((1 << la) - 1), pa0 = t >> la, ppa = 128 >> la;
+    const int jb = t & ((1 << lb) - 1), pb0 = t >> lb, ppb = 128 >> lb;
+    const bool a_two = ja * 8 + 4 < cow, b_two = jb * 8 + 4 < ciw;  // second fp32 chunk of the group exists
+    const int npa = p.TH * 8, npb = p.TH * p.HC;
+    const int ppb_div = ppb / p.HC, ppb_mod = ppb - ppb_div * p.HC;
+    const int pb0_r = pb0 / p.HC, pb0_c = pb0 - pb0_r * p.HC;
+    const float* xb = (const float*)p.x;
+    const float* dyb = (const float*)p.dy;
+    const float* scb = (const float*)d.in_scale;
+    const int tiles_per_img = p.row_tiles * p.col_tiles;
+    int pub = 0, sa_p = 0;
+    uint32_t ph_p = 0;
+
+    auto tile_origin = [&](int i, int& n, int& oy0, int& ox0) {
+      const int64_t tt = t_begin + i;
+      n = (int)(tt / tiles_per_img);
+      const int rem = (int)(tt - (int64_t)n * tiles_per_img);
+      const int tr = rem / p.col_tiles;
+      oy0 = tr * p.TH; ox0 = (rem - tr * p.col_tiles) * 8;
+    };
+    // fp32 x8 (two chunks) -> bf16 hi chunk + bf16 lo chunk
+    auto split8 = [](const uint4& c0v, const uint4& c1v, const float* sv, uint4& hi, uint4& lo) {
+      const float f[8] = {__uint_as_float(c0v.x), __uint_as_float(c0v.y), __uint_as_float(c0v.z), __uint_as_float(c0v.w),
+                          __uint_as_float(c1v.x), __uint_as_float(c1v.y), __uint_as_float(c1v.z), __uint_as_float(c1v.w)};
+      __nv_bfloat16 h[8], l[8];
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        const float v = sv ? f[e] * sv[e] : f[e];
+        h[e] = __float2bfloat16_rn(v);
+        l[e] = __float2bfloat16_rn(v - __bfloat162float(h[e]));
+      }
+      hi = *(const uint4*)h; lo = *(const uint4*)l;
+    };
+
+    auto convert_publish = [&](int i) {                  // tile i has landed in its staging buffer
+      const uint8_t* stg = stg_base + (i % NSTG) * p.stage_bytes;
+      mbar_wait(smem_u32(&empty_bar[sa_p]), ph_p ^ 1);
+      uint8_t* ms = mma_base + sa_p * p.stage_bytes;
+      if (ja < ga) {
+        const uint8_t* src = stg + (2 * ja) * p.a_plane;
+        uint8_t* dst = ms + ja * p.a_plane;
+        for (int pp = pa0; pp < npa; pp += ppa) {
+          const uint4 c0v = *(const uint4*)(src + pp * 16), c1v = *(const uint4*)(src + p.a_plane + pp * 16);
+          uint4 hi, lo;
+          split8(c0v, c1v, nullptr, hi, lo);
+          *(uint4*)(dst + pp * 16) = hi;
+          *(uint4*)(dst + a_half + pp * 16) = lo;
+        }
+      }
+      if (jb < gb) {
+        float sv[8];
+        if (scb) {
+          int n, oy0, ox0;
+          tile_origin(i, n, oy0, ox0);
+          const float* sp = scb + (int64_t)n * d.ci + c0 + jb * 8;
+#pragma unroll
+          for (int e = 0; e < 8; e++) sv[e] = (jb * 8 + e < ciw) ? __ldg(sp + e) : 0.f;
+        }
+        const uint8_t* src = stg + 32 * p.a_plane + (2 * jb) * p.b_plane;
+        uint8_t* dst = ms + 2 * a_half + jb * p.b_plane;
+        int hr = pb0_r, hc = pb0_c;
+        for (int hp = pb0; hp < npb; hp += ppb) {
+          const int slot = (s == 1) ? hc : ((hc & 1) * p.QP + (hc >> 1));
+          const int off = (hr * p.HC + slot) * 16;
+          const uint4 c0v = *(const uint4*)(src + off), c1v = *(const uint4*)(src + p.b_plane + off);
+          uint4 hi, lo;
+          split8(c0v, c1v, scb ? sv : nullptr, hi, lo);
+          *(uint4*)(dst + off) = hi;
+          *(uint4*)(dst + b_half + off) = lo;
+          hr += ppb_div; hc += ppb_mod;
+          if (hc >= p.HC) { hc -= p.HC; hr++; }
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(smem_u32(&full_bar[sa_p]));
+      if (++sa_p == SA) { sa_p = 0; ph_p ^= 1; }
+    };
+
+    for (int i = 0; i < ntiles; i++) {
+      int n, oy0, ox0;
+      tile_origin(i, n, oy0, ox0);
+      const uint32_t a_dst = smem_u32(stg_base + (i % NSTG) * p.stage_bytes);
+      const uint32_t b_dst = a_dst + 32 * p.a_plane;
+      if (ja < ga) {
+        const float* src_n = dyb + (int64_t)n * d.y_strides[0] + o0 + ja * 8;
+        const uint32_t dst_j = a_dst + (2 * ja) * p.a_plane;
+        for (int pp = pa0; pp < npa; pp += ppa) {
+          const int oy = oy0 + (pp >> 3), ox = ox0 + (pp & 7);
+          const bool ok = oy < d.out_h && ox < d.out_w;
+          const float* src = src_n + (int64_t)oy * d.y_strides[2] + (int64_t)ox * d.y_strides[3];
+          cp_async16(dst_j + pp * 16, ok ? (const void*)src : (const void*)dyb, ok ? 16u : 0u);
+          if (a_two) cp_async16(dst_j + p.a_plane + pp * 16, ok ? (const void*)(src + 4) : (const void*)dyb, ok ? 16u : 0u);
+        }
+      }
+      if (jb < gb) {
+        const float* src_n = xb + (int64_t)n * d.x_strides[0] + c0 + jb * 8;
+        const uint32_t dst_j = b_dst + (2 * jb) * p.b_plane;
+        const int ix0 = ox0 * s - d.pad_x;
+        int hr = pb0_r, hc = pb0_c;
+        for (int hp = pb0; hp < npb; hp += ppb) {
+          const int iy = (oy0 + hr) * s + ky - d.pad_y, ix = ix0 + hc;
+          const bool ok = iy >= 0 && iy < d.in_h && ix >= 0 && ix < d.in_w;
+          const int slot = (s == 1) ? hc : ((hc & 1) * p.QP + (hc >> 1));
+          const float* src = src_n + (int64_t)iy * d.x_strides[2] + (int64_t)ix * d.x_strides[3];
+          const uint32_t dd = dst_j + (hr * p.HC + slot) * 16;
+          cp_async16(dd, ok ? (const void*)src : (const void*)xb, ok ? 16u : 0u);
+          if (b_two) cp_async16(dd + p.b_plane, ok ? (const void*)(src + 4) : (const void*)xb, ok ? 16u : 0u);
+          hr += ppb_div; hc += ppb_mod;
+          if (hc >= p.HC) { hc -= p.HC; hr++; }
+        }
+      }
+      cp_async_commit();
+      if (i - pub >= WG_LOOKAHEAD) {
+        cp_async_wait<WG_LOOKAHEAD>();
+        convert_publish(pub++);
+      }
+    }
+    cp_async_wait<0>();
+    while (pub < ntiles) convert_publish(pub++);
+
+    // =========================== epilogue ===========================
+    if (ntiles > 0) {
+      mbar_wait(smem_u32(&accum_bar), 0);
+      tc_fence_after();
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+      const int o = o0 + threadIdx.x;
+      const int wy = d.flip ? d.kh - 1 - ky : ky;
+      for (int kx = 0; kx < d.kw; kx++) {
+        const int wx = d.flip ? d.kw - 1 - kx : kx;
+#pragma unroll 1
+        for (int cc = 0; cc < BNC; cc += 16) {
+          uint32_t acc[16];
+          tmem_ld16(lane_addr + kx * BNC + cc, acc);
+          if (o >= d.co) continue;
+#pragma unroll
+          for (int e = 0; e < 16; e++) {
+            const int c = c0 + cc + e;
+            if (c < d.ci) atomicAdd(p.dw + (((int64_t)o * d.ci + c) * d.kh + wy) * d.kw + wx, __uint_as_float(acc[e]));
+          }
+        }
+      }
+      tc_fence_before();
+    }
+  } else {
+    // =========================== MMA issuer ===========================
+    {
+      const int mmas = p.TH * 8 / KPM;
+      const uint32_t a_hi = smem_desc_hi((uint32_t)p.a_plane), b_hi = smem_desc_hi((uint32_t)p.b_plane);
+      const uint32_t a_lo_base = smem_desc_lo(smem_u32(mma_base), 128);
+      const uint32_t b_lo_base = smem_desc_lo(smem_u32(mma_base) + (uint32_t)(2 * a_half), (uint32_t)(p.HC * 16));
+      const uint32_t stage_u = (uint32_t)p.stage_bytes >> 4;
+      const uint32_t a_half_u = (uint32_t)a_half >> 4, b_half_u = (uint32_t)b_half >> 4;
+      const uint32_t b_row_u = (uint32_t)((KPM / 8) * p.HC);
+      int sa = 0;
+      uint32_t pha = 0;
+      for (int i = 0; i < ntiles; i++) {
+        mbar_wait(smem_u32(&full_bar[sa]), pha);
+        tc_fence_after();
+        const uint32_t a0 = a_lo_base + sa * stage_u, b0 = b_lo_base + sa * stage_u;
+        if (lane == 0) {
+          for (int kx = 0; kx < d.kw; kx++) {
+            const uint32_t bk = b0 + (uint32_t)((kx % s) * p.QP + kx / s);
+            const uint32_t tm = tmem_base + kx * BNC;
+            for (int kk = 0; kk < mmas; kk++) {
+              const uint32_t aa = a0 + kk * KPM, bb = bk + kk * b_row_u;
+              umma_lh<1>(tm, aa, a_hi, bb, b_hi, IDESC, (i > 0 || kk > 0) ? 1u : 0u);               // hi * hi
+              umma_lh<1>(tm, aa, a_hi, bb + b_half_u, b_hi, IDESC, 1u);                             // hi * lo
+              umma_lh<1>(tm, aa + a_half_u, a_hi, bb, b_hi, IDESC, 1u);                             // lo * hi
+            }
+          }
+          umma_commit(smem_u32(&empty_bar[sa]));
+        }
+        __syncwarp();
+        if (++sa == SA) { sa = 0; pha ^= 1; }
+      }
+      if (ntiles > 0 && lane == 0) umma_commit(smem_u32(&accum_bar));
+    }
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
 // ---- host side -------------------------------------------------------------------------------------------
 bool conv_wgrad_halo_eligible(const sgb_conv_desc* d) {
   if (!((d->kh == 3 && d->kw == 3) || (d->kh == 1 && d->kw == 1))) return false;
@@ -306,6 +555,50 @@ static int launch_wgrad_halo(const sgb_conv_desc* d, const void* x, const void* 
   return 0;
 }
 
+template <int BNC>
+static int launch_wgrad_split(const sgb_conv_desc* d, const void* x, const void* dy, float* dw, cudaStream_t st) {
+  WgradHaloParams p; p.d = *d; p.x = x; p.dy = dy; p.dw = dw;
+  const int s = d->stride;
+  p.HC = 7 * s + d->kw;
+  p.QP = (s == 1) ? 0 : (p.HC + 1) / 2;
+  p.ctiles = (d->ci + BNC - 1) / BNC;
+  const int otiles = (d->co + UM - 1) / UM;
+  const int budget = 224 * 1024;
+  const int nstg = WG_LOOKAHEAD + 1;
+  int TH = 8, stages = 0;                               // pixels per tile must be a multiple of 16 (one bf16 MMA): TH >= 2
+  for (;; TH >>= 1) {
+    int npa = TH * 8 + 1;
+    int npb = TH * p.HC; while (npb % 8 != 1) npb++;
+    p.a_plane = npa * 16; p.b_plane = npb * 16;
+    p.a_bytes = 32 * p.a_plane;
+    p.stage_bytes = (p.a_bytes + (BNC / 4) * p.b_plane + 127) / 128 * 128;     // fp32 staging == bf16 hi + lo planes
+    stages = budget / p.stage_bytes - nstg; if (stages > 4) stages = 4;
+    if (stages >= 3 || TH == 2) break;
+  }
+  SGB_REQUIRE(stages >= 2, "wgrad split: tile does not fit shared memory");
+  p.TH = TH; p.stages = stages;
+  p.row_tiles = (d->out_h + TH - 1) / TH; p.col_tiles = (d->out_w + 7) / 8;
+  p.total_tiles = (int64_t)d->n * p.row_tiles * p.col_tiles;
+  const int64_t base = (int64_t)otiles * p.ctiles * d->kh;
+  int64_t splits = kNumSMs / base; if (splits < 1) splits = 1;
+  if (splits > p.total_tiles) splits = p.total_tiles;
+  p.chunk_tiles = ceil_div(p.total_tiles, splits);
+  splits = ceil_div(p.total_tiles, p.chunk_tiles);
+  SGB_REQUIRE((int64_t)p.ctiles * d->kh <= 65535 && splits <= 65535, "problem too large for the wgrad split grid");
+  SGB_REQUIRE(aligned16(x) && aligned16(dy), "x and dy must be 16-byte aligned");
+  const size_t smem = (size_t)(nstg + stages) * p.stage_bytes + 1024;
+  auto kern = conv_wgrad_split_kernel<BNC>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    SGB_REQUIRE(e == cudaSuccess, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    attr_set = true;
+  }
+  kern<<<dim3((unsigned)otiles, (unsigned)(p.ctiles * d->kh), (unsigned)splits), WG_THREADS, smem, st>>>(p);
+  SGB_LAUNCH_CHECK();
+  return 0;
+}
+
 template <class T, int KIND>
 static int dispatch_wgrad_halo(const sgb_conv_desc* d, const void* x, const void* dy, float* dw, cudaStream_t s) {
   if (d->ci <= 32) return launch_wgrad_halo<T, KIND, 32>(d, x, dy, dw, s);
@@ -320,7 +613,10 @@ int conv_wgrad_halo(const sgb_conv_desc* d, const void* x, const void* dy, void*
   if ((int64_t)d->n * d->out_h * d->out_w == 0) return 0;
   if (d->dtype == SGB_F16) return dispatch_wgrad_halo<__half, 0>(d, x, dy, (float*)dw, s);
   if (d->dtype == SGB_BF16) return dispatch_wgrad_halo<__nv_bfloat16, 1>(d, x, dy, (float*)dw, s);
-  return dispatch_wgrad_halo<float, 2>(d, x, dy, (float*)dw, s);
+  // fp32: kind::tf32 does not take MN-major operands in this layout -> 3 x bf16 split kernel
+  if (d->ci <= 32) return launch_wgrad_split<32>(d, x, dy, (float*)dw, s);
+  if (d->ci <= 64) return launch_wgrad_split<64>(d, x, dy, (float*)dw, s);
+  return launch_wgrad_split<128>(d, x, dy, (float*)dw, s);
 }
 
 }  // namespace sgb

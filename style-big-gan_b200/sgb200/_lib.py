@@ -49,6 +49,7 @@ SIGNATURES = {
     'sgb_conv2d_forward': (_int, [_c.POINTER(ConvDesc), _vp, _vp, _vp, _vp]),
     'sgb_conv2d_wgrad': (_int, [_c.POINTER(ConvDesc), _vp, _vp, _vp, _vp]),
     'sgb_conv2d_uses_tensor_cores': (_int, [_c.POINTER(ConvDesc)]),
+    'sgb_conv2d_wgrad_uses_tensor_cores': (_int, [_c.POINTER(ConvDesc)]),
     'sgb_conv2d_workspace_bytes': (_i64, [_c.POINTER(ConvDesc)]),
     'sgb_scale_nc': (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _c.POINTER(_i64), _c.POINTER(_i64), _vp]),
     'sgb_mul_sum_hw': (_int, [_vp, _vp, _vp, _int, _int, _int, _int, _int, _c.POINTER(_i64), _c.POINTER(_i64), _vp]),

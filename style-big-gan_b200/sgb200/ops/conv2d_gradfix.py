@@ -268,7 +268,8 @@ def _conv2d_op(transpose, weight_shape, stride, padding, output_padding, dilatio
                                sc if d.in_scale else None)
             dwf = torch.empty([dy_.shape[1], x_.shape[1] // groups, kh, kw], dtype=_lib.acc_dtype(input.dtype), device=input.device)
             nbytes += dwf.numel() * dwf.element_size()
-            with torch.cuda.device(input.device), _lib.prof('conv_wgrad', flops, nbytes):
+            tc = _lib.lib().sgb_conv2d_wgrad_uses_tensor_cores(d)
+            with torch.cuda.device(input.device), _lib.prof('conv_wgrad_tc' if tc else 'conv_wgrad_simt', flops, nbytes):
                 rc = _lib.lib().sgb_conv2d_wgrad(d, _lib.ptr(x_), _lib.ptr(dy_), _lib.ptr(dwf), _lib.stream_ptr(input.device))
             _lib.check(rc, 'conv2d_wgrad')
             if padded:

@@ -57,6 +57,8 @@ class TrainConfig:
     channels_last: bool = True
     noise_mode: str = 'random'
     seed: int = 0
+    cuda_graphs: bool = False      # capture each training phase in a CUDA graph and replay it (static shapes; removes the
+                                   # per-launch host cost of ~3000 kernel launches per iteration)
 
 
 # named workloads of BASELINE.json `configs`
@@ -101,19 +103,20 @@ class FlatGradAllReduce:
         self.params = [p for p in params]
         self.group = group
 
-    def __call__(self):
+    def __call__(self, grads=None):
+        """grads: explicit list of gradient tensors (the static ones of a captured graph); default = the .grad fields"""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
             return 0
-        ps = [p for p in self.params if p.grad is not None]
-        if not ps:
+        gs = [g for g in grads if g is not None] if grads is not None else [p.grad for p in self.params if p.grad is not None]
+        if not gs:
             return 0
-        flat = torch.cat([p.grad.reshape(-1).to(torch.float32) for p in ps])
+        flat = torch.cat([g.reshape(-1).to(torch.float32) for g in gs])
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
         flat.div_(dist.get_world_size(self.group))
         off = 0
-        for p in ps:
-            n = p.grad.numel()
-            p.grad.copy_(flat[off:off + n].reshape(p.grad.shape))
+        for g in gs:
+            n = g.numel()
+            g.copy_(flat[off:off + n].reshape(g.shape))
             off += n
         return flat.numel()
 
@@ -139,15 +142,19 @@ class Trainer:
                                                 ('D', self.D, cfg.d_reg_interval, cfg.use_r1)]:
             params = list(module.parameters())
             if not has_reg:
-                opt = torch.optim.Adam(params, lr=cfg.lr, betas=tuple(cfg.betas), eps=1e-8, fused=True)
+                opt = torch.optim.Adam(params, lr=cfg.lr, betas=tuple(cfg.betas), eps=1e-8, fused=True, capturable=cfg.cuda_graphs)
                 self.phases.append(dict(name=name + 'main', module=module, opt=opt, interval=1))
             else:
                 r = interval / (interval + 1)
-                opt = torch.optim.Adam(params, lr=cfg.lr * r, betas=tuple(b ** r for b in cfg.betas), eps=1e-8, fused=True)
+                opt = torch.optim.Adam(params, lr=cfg.lr * r, betas=tuple(b ** r for b in cfg.betas), eps=1e-8, fused=True,
+                                       capturable=cfg.cuda_graphs)
                 self.phases.append(dict(name=name + 'main', module=module, opt=opt, interval=1))
                 self.phases.append(dict(name=name + 'reg', module=module, opt=opt, interval=interval))
         for ph in self.phases:
             ph['sync'] = FlatGradAllReduce(ph['module'].parameters())
+        # CUDA-graph state (cfg.cuda_graphs): static inputs, one graph pair per phase, shared memory pool
+        self._graphs = None
+        self.replayed_launches = 0      # libsgb200 kernel launches executed through graph replays
 
     # ---- forward helpers (losses_base.py:131-156)
     def run_G(self, z, return_ws=False):
@@ -208,7 +215,8 @@ class Trainer:
         (real_logits * 0 + loss.unsqueeze(1)).mean().mul(gain).backward()
         return loss.detach().mean()
 
-    def run_phase(self, ph, real, z):
+    def _phase_grads(self, ph, real, z):
+        """forward + backward of one phase: leaves the gradients in .grad, returns the loss value"""
         opt, module = ph['opt'], ph['module']
         opt.zero_grad(set_to_none=True)
         module.requires_grad_(True)
@@ -223,17 +231,107 @@ class Trainer:
         else:
             val = self.phase_Dreg(real, gain)
         module.requires_grad_(False)
-        ph['sync']()
-        for p in module.parameters():
-            if p.grad is not None:
-                torch.nan_to_num(p.grad, nan=0, posinf=1e5, neginf=-1e5, out=p.grad)
-        opt.step()
         return val
 
-    def iteration(self, real_u8, force_all_phases=False):
-        """real_u8: uint8 [batch_gpu, C, R, R] already on the device."""
+    def _phase_update(self, ph):
+        for p in ph['module'].parameters():
+            if p.grad is not None:
+                torch.nan_to_num(p.grad, nan=0, posinf=1e5, neginf=-1e5, out=p.grad)
+        ph['opt'].step()
+
+    def run_phase(self, ph, real, z):
+        val = self._phase_grads(ph, real, z)
+        ph['sync']()
+        self._phase_update(ph)
+        return val
+
+    # ---- CUDA graphs: every phase is static-shaped, so its ~1000 launches are captured once and replayed ----
+    def _real_from_u8(self, real_u8):
+        return real_u8.to(torch.float32) / 127.5 - 1            # trainers.py:716
+
+    def _ema_update(self):
         cfg = self.cfg
-        real = real_u8.to(torch.float32) / 127.5 - 1            # trainers.py:716
+        ema_nimg = cfg.ema_kimg * 1000
+        beta = 0.5 ** (cfg.batch_gpu * self.world_size / max(ema_nimg, 1e-8))
+        with torch.no_grad():
+            ps = list(self.G.parameters())
+            pe = list(self.G_ema.parameters())
+            torch._foreach_lerp_(pe, ps, 1 - beta)           # p_ema = p.lerp(p_ema, beta)
+            for b_ema, b in zip(self.G_ema.buffers(), self.G.buffers()):
+                b_ema.copy_(b)
+
+    def _build_graphs(self, real_u8):
+        from . import _lib
+        cfg = self.cfg
+        dev = self.device
+        multi = self.world_size > 1
+        st = dict(real_u8=torch.empty_like(real_u8), graphs={}, pool=None)
+        st['real_u8'].copy_(real_u8)
+        # eager warm-up on a side stream: lazy initialisation (optimizer state, kernel attributes, library handles)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                real = self._real_from_u8(st['real_u8'])
+                for ph in self.phases:
+                    z = torch.randn([cfg.batch_gpu, cfg.z_dim], device=dev)
+                    self.run_phase(ph, real, z)
+                if self.G_ema is not None:
+                    self._ema_update()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        pool = torch.cuda.graph_pool_handle()
+        for ph in self.phases:
+            g1 = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(g1, pool=pool):
+                real = self._real_from_u8(st['real_u8'])
+                z = torch.randn([cfg.batch_gpu, cfg.z_dim], device=dev)
+                val = self._phase_grads(ph, real, z)
+                if not multi:
+                    self._phase_update(ph)
+            grads = [p.grad for p in ph['module'].parameters()]      # this graph's static gradient tensors
+            g2 = None
+            if multi:       # the gradient all-reduce runs between the two graphs (eagerly, on NCCL's terms)
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2, pool=pool):
+                    self._phase_update(ph)
+            st['graphs'][ph['name']] = (g1, g2, val, _lib.launch_count() - n0, grads)
+        if self.G_ema is not None:
+            ge = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ge, pool=pool):
+                self._ema_update()
+            st['ema'] = ge
+        self._graphs = st
+
+    def _graph_iteration(self, real_u8, force_all_phases):
+        if self._graphs is None:
+            self._build_graphs(real_u8)
+        st = self._graphs
+        st['real_u8'].copy_(real_u8, non_blocking=True)
+        out = {}
+        for ph in self.phases:
+            if not force_all_phases and self.batch_idx % ph['interval'] != 0:
+                continue
+            g1, g2, val, launches, grads = st['graphs'][ph['name']]
+            g1.replay()
+            if g2 is not None:
+                ph['sync'](grads)
+                g2.replay()
+            self.replayed_launches += launches
+            out[ph['name']] = val
+        if self.G_ema is not None:
+            st['ema'].replay()
+        self.batch_idx += 1
+        return out
+
+    def iteration(self, real_u8, force_all_phases=False, eager=False):
+        """real_u8: uint8 [batch_gpu, C, R, R] already on the device.  With cfg.cuda_graphs (and not `eager`) the
+        returned loss tensors are the graphs' static outputs (overwritten by the next iteration)."""
+        cfg = self.cfg
+        if cfg.cuda_graphs and not eager:
+            return self._graph_iteration(real_u8, force_all_phases)
+        real = self._real_from_u8(real_u8)
         out = {}
         zs = torch.randn([len(self.phases), cfg.batch_gpu, cfg.z_dim], device=self.device)
         for ph, z in zip(self.phases, zs):
@@ -241,13 +339,6 @@ class Trainer:
                 continue
             out[ph['name']] = self.run_phase(ph, real, z)
         if self.G_ema is not None:
-            ema_nimg = cfg.ema_kimg * 1000
-            beta = 0.5 ** (cfg.batch_gpu * self.world_size / max(ema_nimg, 1e-8))
-            with torch.no_grad():
-                ps = list(self.G.parameters())
-                pe = list(self.G_ema.parameters())
-                torch._foreach_lerp_(pe, ps, 1 - beta)           # p_ema = p.lerp(p_ema, beta)
-                for b_ema, b in zip(self.G_ema.buffers(), self.G.buffers()):
-                    b_ema.copy_(b)
+            self._ema_update()
         self.batch_idx += 1
         return out

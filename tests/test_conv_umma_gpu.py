@@ -141,9 +141,13 @@ def test_umma_wgrad_vs_oracle(dtype, case):
     w = (torch.randn(co, ci, k, k) / math.sqrt(ci * k * k)).to(DEV, dtype).requires_grad_(True)
     s = (torch.randn(n, ci) + 1).to(DEV)
     for scale in (None, s):
+        from sgb200 import _lib
         y = cg.conv2d(x, w, stride=stride, padding=pad, in_scale=scale)
-        dy = torch.randn(y.shape).to(DEV, dtype)
+        dy = _cl(torch.randn(y.shape).to(DEV, dtype))          # gradients arrive channels_last in the networks
+        _lib.profile_start()
         dw, = torch.autograd.grad(y, [w], dy)
+        torch.cuda.synchronize()
+        assert set(_lib.profile_stop().summary()) == {'conv_wgrad_tc'}
         xo = x.cpu().float() * (1 if scale is None else scale.cpu()[:, :, None, None])
         wo = w.detach().cpu().float().requires_grad_(True)
         yo = torch.nn.functional.conv2d(xo, wo, stride=stride, padding=pad)
@@ -155,7 +159,7 @@ def test_umma_wgrad_vs_oracle(dtype, case):
             dw1, = torch.autograd.grad(cg.conv2d(x, w, stride=stride, padding=pad, in_scale=scale), [w], dy)
         finally:
             cg.use_halo_kernel = True
-        assert_close(dw, dw1.float().cpu(), 3e-3, f'{case} {dtype} halo vs per-tap wgrad')
+        assert_close(dw, dw1.float().cpu(), 1e-2 if dtype == torch.bfloat16 else 3e-3, f'{case} {dtype} halo vs per-tap wgrad')
 
 
 @pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16, torch.float32])
@@ -243,7 +247,7 @@ def test_channel_padding_makes_small_channel_convs_tensor_core(dtype, case):
     dx, dw = torch.autograd.grad(y, [x, w], dy)
     torch.cuda.synchronize()
     kinds = set(_lib.profile_stop().summary())
-    assert 'conv_fwd_simt' not in kinds, kinds          # forward and dgrad both on tensor cores
+    assert 'conv_fwd_simt' not in kinds and 'conv_wgrad_simt' not in kinds, kinds      # all three on tensor cores
     xo = x.detach().cpu().float().requires_grad_(True)
     wo = w.detach().cpu().float().requires_grad_(True)
     yo = torch.nn.functional.conv2d(xo, wo, padding=pad)
