@@ -169,6 +169,7 @@ def main():
     ap.add_argument('--no-graphs', action='store_true', help='launch every kernel eagerly instead of replaying per-phase CUDA graphs')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-roofline', action='store_true', help='skip the eager per-kernel timing loop (ncu launch-list runs)')
     ap.add_argument('--breakdown', default=None, help='write the per-kernel-family time table (json) here')
     args = ap.parse_args()
 
@@ -213,11 +214,13 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         last = None
+        torch.cuda.nvtx.range_push('sgb_timed')           # ncu --nvtx --nvtx-include "sgb_timed/" profiles this loop only
         for _ in range(steps):
             real = host_real.to(device, non_blocking=True) if from_host else dev_real
             out = tr.iteration(real, eager=profile)      # per-launch events need eager launches
             if from_host:
                 last = {k: float(v) for k, v in out.items()}      # D2H read of every loss of the step
+        torch.cuda.nvtx.range_pop()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -241,7 +244,9 @@ def main():
     clocks = sampler.stop() if sampler else None
     # per-kernel-family device time (roofline leg): the same K steps launched eagerly with CUDA events around
     # every libsgb200 launch; not part of the reported step time
-    _, _, summ, _ = timed_loop(args.steps, from_host=False, profile=True)
+    summ = None
+    if not args.no_roofline:
+        _, _, summ, _ = timed_loop(args.steps, from_host=False, profile=True)
 
     e2e = None
     if not args.no_e2e:
@@ -256,25 +261,31 @@ def main():
 
     peaks = load_peaks()
     value = args.steps * N * world / (ms / 1000.0)
-    # dominant kernel family by device time
-    total_ms = sum(d['ms'] for d in summ.values()) or 1.0
-    dom = max(summ, key=lambda k: summ[k]['ms'])
-    d = summ[dom]
-    if dom.startswith('conv'):
-        ach = d['flops'] / (d['ms'] / 1000.0) / 1e12
-        roof = dict(kernel=dom, bound='tensor', achieved=ach, peak=peaks['tc_sustained'], unit='TFLOP/s', frac=ach / peaks['tc_sustained'],
-                    traffic=None, peak_source=peaks['source'] + ' bf16 sustained', launches=d['launches'],
-                    avg_launch_ms=d['ms'] / d['launches'], share_of_kernel_time=d['ms'] / total_ms)
-    else:
-        ach = d['bytes'] / (d['ms'] / 1000.0) / 1e9
-        roof = dict(kernel=dom, bound='hbm', achieved=ach, peak=peaks['hbm'], unit='GB/s', frac=ach / peaks['hbm'], traffic=None,
-                    peak_source=peaks['source'], launches=d['launches'], avg_launch_ms=d['ms'] / d['launches'],
-                    share_of_kernel_time=d['ms'] / total_ms)
-    if args.breakdown:
-        os.makedirs(os.path.dirname(os.path.abspath(args.breakdown)), exist_ok=True)
-        with open(args.breakdown, 'w') as f:
-            json.dump(dict(step_ms=ms / args.steps, kernel_ms_per_step={k: v['ms'] / args.steps for k, v in summ.items()},
-                           detail=summ), f, indent=1)
+    # dominant kernel family by device time (eager loop, CUDA events around every libsgb200 launch)
+    roof = None
+    if summ:
+        total_ms = sum(d['ms'] for d in summ.values()) or 1.0
+        dom = max(summ, key=lambda k: summ[k]['ms'])
+        d = summ[dom]
+        if dom.startswith('conv'):
+            # fp32 tensors run TF32 MMAs (half the bf16 rate) in the forward / data-gradient kernels
+            tf32 = cfg.num_fp16_res == 0 and args.fp32_mode == 'tf32' and dom.startswith('conv_fwd')
+            peak = peaks['tc_sustained'] / (2 if tf32 else 1)
+            ach = d['flops'] / (d['ms'] / 1000.0) / 1e12
+            roof = dict(kernel=dom, bound='tensor', achieved=ach, peak=peak, unit='TFLOP/s', frac=ach / peak, traffic=None,
+                        peak_source=peaks['source'] + (' bf16 sustained / 2 (TF32 MMA rate)' if tf32 else ' bf16 sustained'),
+                        launches=d['launches'], avg_launch_ms=d['ms'] / d['launches'], share_of_kernel_time=d['ms'] / total_ms,
+                        algorithmic_flops_per_launch=d['flops'] / d['launches'])
+        else:
+            ach = d['bytes'] / (d['ms'] / 1000.0) / 1e9
+            roof = dict(kernel=dom, bound='hbm', achieved=ach, peak=peaks['hbm'], unit='GB/s', frac=ach / peaks['hbm'], traffic=None,
+                        peak_source=peaks['source'], launches=d['launches'], avg_launch_ms=d['ms'] / d['launches'],
+                        share_of_kernel_time=d['ms'] / total_ms, algorithmic_bytes_per_launch=d['bytes'] / d['launches'])
+        if args.breakdown:
+            os.makedirs(os.path.dirname(os.path.abspath(args.breakdown)), exist_ok=True)
+            with open(args.breakdown, 'w') as f:
+                json.dump(dict(step_ms=ms / args.steps, kernel_ms_per_step={k: v['ms'] / args.steps for k, v in summ.items()},
+                               detail=summ), f, indent=1)
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
