@@ -52,6 +52,30 @@ def main():
         x, w = conv_case(8, 64, 256, torch.float32)
         return (lambda: conv2d_gradfix.conv2d(x, w, padding=1)), 2.0 * 8 * 256 * 256 * 64 * 64 * 9, 2 * x.numel() * 4
 
+    @case('fused_act_f32_c64_256')
+    def _():
+        from sgb200.ops import fused_conv
+        x, w = conv_case(8, 64, 256, torch.float32)
+        b = torch.randn(64, device=DEV)
+        return (lambda: fused_conv.conv2d_bias_act(x, w, b, padding=1, act='lrelu', clamp=256)), 2.0 * 8 * 256 * 256 * 64 * 64 * 9, 2 * x.numel() * 4
+
+    @case('fused_mod_f32_c64_256')
+    def _():
+        from sgb200.ops import fused_conv
+        x, w = conv_case(8, 64, 256, torch.float32)
+        b = torch.randn(64, device=DEV)
+        s = torch.randn(8, 64, device=DEV) + 1
+        dc = torch.rand(8, 64, device=DEV) + 0.5
+        nz = torch.randn(8, 1, 256, 256, device=DEV)
+        return (lambda: fused_conv.conv2d_bias_act(x, w, b, padding=1, styles=s, dcoefs=dc, noise=nz, act='lrelu', clamp=256)), \
+            2.0 * 8 * 256 * 256 * 64 * 64 * 9, 2 * x.numel() * 4
+
+    @case('scaled_f32_c64_256')
+    def _():
+        x, w = conv_case(8, 64, 256, torch.float32)
+        s = torch.randn(8, 64, device=DEV) + 1
+        return (lambda: conv2d_gradfix.conv2d(x, w, padding=1, in_scale=s)), 2.0 * 8 * 256 * 256 * 64 * 64 * 9, 2 * x.numel() * 4
+
     @case('fwd_f32_c128_128')
     def _():
         x, w = conv_case(8, 128, 128, torch.float32)

@@ -124,6 +124,18 @@ int sgb_mul_sum_hw(const void* a, const void* b, void* out, int dtype, int n, in
 int sgb_sum_c(const void* a, void* out, int dtype, int n, int c, int h, int w, const int64_t a_strides[4],
               void* stream);
 
+/* ---- backward of the convolution's fused epilogue (sgb_conv_desc: out_scale / noise / bias / act / gain / clamp) ----
+ * One pass over channels_last (dy, y) replacing bias_act backward + its bias sum (bias_act.py:161-175) and the fma
+ * backward passes (fma.py:37-58):   dz = dy * gain * act'(y), masked where |y| >= clamp;
+ *   dconv = dz * out_scale[n,c]  (dtype of y);   dbias[c] = sum dz;   dnoise[n,hw] = sum_c dz;
+ *   dscale[n,c] = sum_hw dz * conv, conv re-derived from y.   bias / out_scale / noise / dbias / dnoise / dscale may be NULL;
+ * y may be NULL for a linear epilogue without clamp and without dscale (nothing depends on it: the reference does not
+ * keep y for linear either, bias_act.py:152-155, which is what lets callers add to the output in place);
+ * the three reduction outputs are fp32 and are overwritten.  act: SGB_ACT_LINEAR or SGB_ACT_LRELU. */
+int sgb_fused_epilogue_bwd(const void* dy, const void* y, void* dconv, const void* bias, const void* out_scale,
+                           const void* noise, void* dbias, void* dnoise, void* dscale, int dtype, int n, int c, int hw,
+                           int act, float alpha, float gain, float clamp, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

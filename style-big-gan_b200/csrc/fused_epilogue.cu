@@ -1,0 +1,140 @@
+// Backward of the convolution's fused epilogue  y = clamp(lrelu|linear(conv * out_scale[n,c] + noise[n,h,w] + bias[c]) * gain)
+// in ONE pass over (dy, y) -- channels_last tensors, C a multiple of one 16-byte vector.
+//
+// The reference runs this as five activation-sized passes (bias_act backward bias_act.py:161-175 + `dx.sum` for db,
+// fma backward fma.py:37-58: dy * dcoefs, sum(dy * x) for d(dcoefs), sum_c(dy) for d(noise)).  Here:
+//     dz      = dy * gain * (y > 0 ? 1 : alpha), 0 where |y| >= clamp       (bias_act.cu:141: mask on the stored output)
+//     dconv   = dz * out_scale[n,c]                                -> written (the only activation-sized output)
+//     dbias   = sum_{n,h,w} dz                                     -> [C]      (red.add after a block reduction)
+//     dnoise  = sum_c dz                                           -> [N,H,W]  (red.add, one per thread per pixel)
+//     dscale  = sum_{h,w} dz * conv,  conv = (z - noise - bias) / out_scale,  z = y / gain (y > 0) or y / (gain * alpha)
+//               -> [N,C]  -- the pre-activation is re-derived from y (exact where it matters: clamped elements have dz = 0),
+//               so the convolution output never has to be stored
+// All reduction outputs are fp32 and must be zeroed by the caller... no: they are zeroed here (cudaMemsetAsync).
+#include "common.cuh"
+
+namespace sgb {
+
+struct FusedBwdParams {
+  const void* dy; const void* y; void* dconv;
+  const void* bias; const float* out_scale; const float* noise;
+  float* dbias; float* dnoise; float* dscale;
+  int n, c, hw;
+  float alpha, gain, clamp;
+  int ppb;            // pixels per block (all of one image)
+  int blocks_per_img;
+};
+
+// block = 256 threads: thread -> (channel vector cv = tid % CVT, pixel lane pl = tid / CVT); CVT = c / VEC <= 256
+template <class T>
+__global__ void __launch_bounds__(256) fused_epilogue_bwd_kernel(FusedBwdParams p) {
+  constexpr int VEC = Vec16<T>::N;
+  __shared__ float red[256 * 2];
+  const int cvt = p.c / VEC;
+  const int lanes = 256 / cvt;                        // pixel lanes per block
+  const int cv = threadIdx.x % cvt, pl = threadIdx.x / cvt;
+  const int n = blockIdx.x / p.blocks_per_img;
+  const int p0 = (blockIdx.x - n * p.blocks_per_img) * p.ppb;
+  const int p1 = (p0 + p.ppb < p.hw) ? p0 + p.ppb : p.hw;
+  const int c0 = cv * VEC;
+  const bool active = pl < lanes;
+  float sc[VEC], bs[VEC], inv_sc[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; j++) {
+    sc[j] = p.out_scale ? p.out_scale[(int64_t)n * p.c + c0 + j] : 1.f;
+    inv_sc[j] = 1.f / sc[j];
+    bs[j] = p.bias ? to_acc<T>(((const T*)p.bias)[c0 + j]) : 0.f;
+  }
+  // clamp rounded to the storage type, like bias_act.cu, so that saturated 16-bit outputs are recognised
+  const float clampr = p.clamp >= 0.f ? to_acc<T>(from_acc<T>(p.clamp)) : -1.f;
+  const float inv_g = 1.f / p.gain, inv_ga = (p.alpha != 0.f) ? 1.f / (p.gain * p.alpha) : 0.f;
+  float accb[VEC], accs[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; j++) { accb[j] = 0.f; accs[j] = 0.f; }
+  const int64_t img = (int64_t)n * p.hw;
+  if (active) {
+    for (int px = p0 + pl; px < p1; px += lanes) {
+      const int64_t v = (img + px) * cvt + cv;
+      Vec16<T> dyv, yv, out;
+      dyv.raw = ld_stream((const uint4*)p.dy + v);
+      if (p.y) yv.raw = ld_stream((const uint4*)p.y + v);
+      const float nz = p.noise ? p.noise[img + px] : 0.f;
+      float dn = 0.f;
+#pragma unroll
+      for (int j = 0; j < VEC; j++) {
+        const float yy = p.y ? to_acc<T>(yv.v[j]) : 1.f;       // y not kept (linear, no clamp, no dscale): slope 1, never masked
+        const bool pos = yy > 0.f;
+        float dz = to_acc<T>(dyv.v[j]) * p.gain * (pos ? 1.f : p.alpha);
+        if (clampr >= 0.f && !(yy > -clampr && yy < clampr)) dz = 0.f;
+        const float z = yy * (pos ? inv_g : inv_ga);
+        accb[j] += dz;
+        accs[j] += dz * (z - nz - bs[j]) * inv_sc[j];
+        dn += dz;
+        out.v[j] = from_acc<T>(dz * sc[j]);
+      }
+      st_stream((uint4*)p.dconv + v, out.raw);
+      if (p.dnoise) atomicAdd(p.dnoise + img + px, dn);
+    }
+  }
+  // reduce the per-thread channel sums over the pixel lanes of the block, then one red.add per channel per block
+  if (p.dbias || p.dscale) {
+#pragma unroll
+    for (int j = 0; j < VEC; j++) {
+      __syncthreads();
+      red[threadIdx.x] = active ? accb[j] : 0.f;
+      red[256 + threadIdx.x] = active ? accs[j] : 0.f;
+      __syncthreads();
+      if (pl == 0) {
+        float sb = 0.f, ss = 0.f;
+        for (int l = 0; l < lanes; l++) { sb += red[l * cvt + cv]; ss += red[256 + l * cvt + cv]; }
+        if (p.dbias) atomicAdd(p.dbias + c0 + j, sb);
+        if (p.dscale) atomicAdd(p.dscale + (int64_t)n * p.c + c0 + j, ss);
+      }
+    }
+  }
+}
+
+}  // namespace sgb
+
+using namespace sgb;
+
+extern "C" int sgb_fused_epilogue_bwd(const void* dy, const void* y, void* dconv, const void* bias, const void* out_scale,
+                                      const void* noise, void* dbias, void* dnoise, void* dscale, int dtype, int n, int c, int hw,
+                                      int act, float alpha, float gain, float clamp, void* stream) {
+  SGB_REQUIRE(dtype == SGB_F32 || dtype == SGB_F16 || dtype == SGB_BF16, "unsupported dtype");
+  SGB_REQUIRE(act == SGB_ACT_LINEAR || act == SGB_ACT_LRELU, "only linear and lrelu epilogues are fused");
+  SGB_REQUIRE(n >= 0 && c >= 1 && hw >= 0, "bad sizes");
+  const int vec = dtype == SGB_F32 ? 4 : 8;
+  SGB_REQUIRE(c % vec == 0 && c / vec <= 256, "channels must be a multiple of one 16-byte vector (and at most 256 vectors)");
+  SGB_REQUIRE(gain != 0.f, "gain must not be zero");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dbias) SGB_REQUIRE(cudaMemsetAsync(dbias, 0, sizeof(float) * c, s) == cudaSuccess, "memset failed");
+  if (dscale) SGB_REQUIRE(cudaMemsetAsync(dscale, 0, sizeof(float) * (size_t)n * c, s) == cudaSuccess, "memset failed");
+  if (dnoise) SGB_REQUIRE(cudaMemsetAsync(dnoise, 0, sizeof(float) * (size_t)n * hw, s) == cudaSuccess, "memset failed");
+  if ((int64_t)n * hw == 0) return 0;
+  SGB_REQUIRE(dy && dconv, "dy and dconv must not be NULL");
+  SGB_REQUIRE(y || (act == SGB_ACT_LINEAR && clamp < 0.f && !dscale), "y may only be NULL for a linear epilogue without clamp and without dscale");
+  SGB_REQUIRE(aligned16(dy) && aligned16(y) && aligned16(dconv), "tensors must be 16-byte aligned");
+  FusedBwdParams p;
+  p.dy = dy; p.y = y; p.dconv = dconv; p.bias = bias; p.out_scale = (const float*)out_scale; p.noise = (const float*)noise;
+  p.dbias = (float*)dbias; p.dnoise = (float*)dnoise; p.dscale = (float*)dscale;
+  p.n = n; p.c = c; p.hw = hw;
+  p.alpha = (act == SGB_ACT_LINEAR) ? 1.f : alpha; p.gain = gain; p.clamp = clamp;
+  // ~4 blocks per SM in total, whole blocks inside one image
+  const int cvt = c / vec, lanes = 256 / cvt;
+  int64_t want = ((int64_t)kNumSMs * 4 + n - 1) / n;               // blocks per image
+  int64_t maxb = ((int64_t)hw + lanes - 1) / lanes;                // at least one pixel per lane
+  if (want > maxb) want = maxb;
+  if (want < 1) want = 1;
+  p.ppb = (int)(((int64_t)hw + want - 1) / want);
+  p.blocks_per_img = (hw + p.ppb - 1) / p.ppb;
+  const int64_t grid = (int64_t)n * p.blocks_per_img;
+  SGB_REQUIRE(grid <= 0x7fffffff, "grid too large");
+  switch (dtype) {
+    case SGB_F32:  fused_epilogue_bwd_kernel<float><<<(unsigned)grid, 256, 0, s>>>(p); break;
+    case SGB_F16:  fused_epilogue_bwd_kernel<__half><<<(unsigned)grid, 256, 0, s>>>(p); break;
+    default:       fused_epilogue_bwd_kernel<__nv_bfloat16><<<(unsigned)grid, 256, 0, s>>>(p); break;
+  }
+  SGB_LAUNCH_CHECK();
+  return 0;
+}

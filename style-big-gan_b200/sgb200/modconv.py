@@ -34,6 +34,8 @@ def modulated_conv2d(
     demodulate      = True,
     flip_weight     = True,
     fused_modconv   = True,
+    epilogue        = None,     # extension (default off): (bias, act, gain, clamp) of the bias_act that follows; fused into the
+                                # convolution kernel together with demodulation and noise (ops/fused_conv.py)
 ):
     batch_size = x.shape[0]
     out_channels, in_channels, kh, kw = weight.shape
@@ -50,6 +52,11 @@ def modulated_conv2d(
         wsq = weight.square().sum(dim=[2, 3])                                  # [O, I]
         dcoefs = (styles.square() @ wsq.t() + 1e-8).rsqrt()                    # [N, O]
 
+    if not fused_modconv and epilogue is not None:
+        b, act, gain, clamp = epilogue
+        ep = _cr.Epilogue(b=b, act=act, gain=gain, clamp=clamp, dcoefs=dcoefs, noise=noise)
+        return _cr.conv2d_resample(x=x, w=weight.to(x.dtype), f=resample_filter, up=up, down=down, padding=padding,
+                                   flip_weight=flip_weight, in_scale=styles, epilogue=ep)
     if not fused_modconv:
         x = _cr.conv2d_resample(x=x, w=weight.to(x.dtype), f=resample_filter, up=up, down=down, padding=padding,
                                 flip_weight=flip_weight, in_scale=styles)
@@ -74,4 +81,8 @@ def modulated_conv2d(
     x = x.reshape(batch_size, -1, *x.shape[2:])
     if noise is not None:
         x = x.add_(noise)
+    if epilogue is not None:
+        from .ops import bias_act as _ba
+        b, act, gain, clamp = epilogue
+        x = _ba.bias_act(x, b, act=act, gain=gain, clamp=clamp)
     return x

@@ -76,10 +76,11 @@ class Conv2dLayer(torch.nn.Module):
     def forward(self, x, gain=1):
         w = (self.weight * self.weight_gain).to(x.dtype)
         b = self.bias.to(x.dtype) if self.bias is not None else None
-        x = conv2d_resample.conv2d_resample(x=x, w=w, f=self.resample_filter, up=self.up, down=self.down,
-                                            padding=self.padding, flip_weight=(self.up == 1))
         clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
-        return bias_act.bias_act(x, b, act=self.activation, gain=self.act_gain * gain, clamp=clamp)
+        # conv2d_resample -> bias_act (discriminators.py:118-123) with the bias_act in the convolution's epilogue
+        ep = conv2d_resample.Epilogue(b=b, act=self.activation, gain=self.act_gain * gain, clamp=clamp)
+        return conv2d_resample.conv2d_resample(x=x, w=w, f=self.resample_filter, up=self.up, down=self.down,
+                                               padding=self.padding, flip_weight=(self.up == 1), epilogue=ep)
 
 
 class MappingNetwork(torch.nn.Module):
@@ -147,10 +148,11 @@ class SynthesisLayer(torch.nn.Module):
             noise = torch.randn([x.shape[0], 1, self.resolution, self.resolution], device=x.device) * self.noise_strength
         if self.use_noise and noise_mode == 'const':
             noise = self.noise_const * self.noise_strength
-        x = modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=noise, up=self.up, padding=self.padding,
-                             resample_filter=self.resample_filter, flip_weight=(self.up == 1), fused_modconv=fused_modconv)
         clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
-        return bias_act.bias_act(x, self.bias.to(x.dtype), act=self.activation, gain=self.act_gain * gain, clamp=clamp)
+        # modulated_conv2d -> bias_act (generators.py:323-328); demodulation, noise and bias_act run in the conv epilogue
+        return modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=noise, up=self.up, padding=self.padding,
+                                resample_filter=self.resample_filter, flip_weight=(self.up == 1), fused_modconv=fused_modconv,
+                                epilogue=(self.bias.to(x.dtype), self.activation, self.act_gain * gain, clamp))
 
 
 class ToRGBLayer(torch.nn.Module):
@@ -164,8 +166,8 @@ class ToRGBLayer(torch.nn.Module):
 
     def forward(self, x, w, fused_modconv=True):
         styles = self.affine(w) * self.weight_gain
-        x = modulated_conv2d(x=x, weight=self.weight, styles=styles, demodulate=False, fused_modconv=fused_modconv)
-        return bias_act.bias_act(x, self.bias.to(x.dtype), clamp=self.conv_clamp)
+        return modulated_conv2d(x=x, weight=self.weight, styles=styles, demodulate=False, fused_modconv=fused_modconv,
+                                epilogue=(self.bias.to(x.dtype), 'linear', None, self.conv_clamp))
 
 
 class SynthesisBlock(torch.nn.Module):

@@ -306,5 +306,7 @@ def _conv2d_op(transpose, weight_shape, stride, padding, output_padding, dilatio
                         grad2_scale = _fma.mul_sum_hw(g, input).to(in_scale.dtype)
             return grad2_grad_output, grad2_input, grad2_scale
 
+    Conv2d.grad_weight_op = Conv2dGradWeight
+    Conv2d.calc_output_padding = staticmethod(calc_output_padding)
     _cache[key] = Conv2d
     return Conv2d

@@ -20,8 +20,36 @@ def _get_weight_shape(w):
     return [int(sz) for sz in w.shape]
 
 
-def _conv2d_wrapper(x, w, stride=1, padding=0, groups=1, transpose=False, flip_weight=True, in_scale=None):
+class Epilogue:
+    """What the layer runs after the convolution (extension, default off): `y * dcoefs[n,c] + noise`, then
+    bias_act(b, act, gain, clamp).  When the convolution is the LAST stage of the resampling decomposition it is fused
+    into the convolution kernel (ops/fused_conv.py); otherwise it is applied with the stand-alone ops."""
+    def __init__(self, b=None, act='linear', alpha=None, gain=None, clamp=None, dcoefs=None, noise=None):
+        self.b, self.act, self.alpha, self.gain, self.clamp, self.dcoefs, self.noise = b, act, alpha, gain, clamp, dcoefs, noise
+
+    def apply(self, y):
+        from . import bias_act
+        noise = self.noise
+        if noise is not None:
+            noise = noise.to(y.dtype)
+            if noise.ndim < 4 or noise.shape[0] != y.shape[0]:
+                noise = noise.expand(y.shape[0], 1, y.shape[2], y.shape[3])
+        if self.dcoefs is not None:
+            y = _fma.scale_nc(y, self.dcoefs, noise)
+        elif noise is not None:
+            y = y.add_(noise)
+        return bias_act.bias_act(y, self.b, act=self.act, alpha=self.alpha, gain=self.gain, clamp=self.clamp)
+
+
+def _conv2d_wrapper(x, w, stride=1, padding=0, groups=1, transpose=False, flip_weight=True, in_scale=None, epilogue=None):
     """conv2d() is a correlation: flip_weight=True means "use w as is" (reference :29-54)."""
+    if epilogue is not None:
+        if not transpose and groups == 1:
+            from . import fused_conv
+            e = epilogue
+            return fused_conv.conv2d_bias_act(x, w, e.b, stride=stride, padding=padding, flip_weight=flip_weight, styles=in_scale,
+                                              dcoefs=e.dcoefs, noise=e.noise, act=e.act, alpha=e.alpha, gain=e.gain, clamp=e.clamp)
+        return epilogue.apply(_conv2d_wrapper(x, w, stride, padding, groups, transpose, flip_weight, in_scale))
     op = conv2d_gradfix.conv_transpose2d if transpose else conv2d_gradfix.conv2d
     if transpose and in_scale is not None:      # the transposed kernel's weight gradient has no fused scale
         x = _fma.scale_nc(x, in_scale)
@@ -29,7 +57,8 @@ def _conv2d_wrapper(x, w, stride=1, padding=0, groups=1, transpose=False, flip_w
     return op(x, w, stride=stride, padding=padding, groups=groups, flip_weight=(not flip_weight), in_scale=in_scale)
 
 
-def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight=True, flip_filter=False, *, in_scale=None):
+def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight=True, flip_filter=False, *, in_scale=None,
+                    epilogue=None):
     assert isinstance(x, torch.Tensor) and (x.ndim == 4)
     assert isinstance(w, torch.Tensor) and (w.ndim == 4) and (w.dtype == x.dtype)
     assert f is None or (isinstance(f, torch.Tensor) and f.ndim in [1, 2] and f.dtype == torch.float32)
@@ -51,7 +80,8 @@ def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight
         px1 += (fw - down) // 2
         py0 += (fh - down + 1) // 2
         py1 += (fh - down) // 2
-    conv = dict(groups=groups, flip_weight=flip_weight)
+    conv = dict(groups=groups, flip_weight=flip_weight, epilogue=epilogue)      # cases whose last stage is the convolution
+    tail = (lambda y: y) if epilogue is None else epilogue.apply                 # cases that end with a FIR pass
 
     # 1x1 conv + downsampling: filter/decimate first, then convolve
     if kw == 1 and kh == 1 and (down > 1 and up == 1):
@@ -62,8 +92,8 @@ def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight
 
     # 1x1 conv + upsampling: convolve first, then upsample
     if kw == 1 and kh == 1 and (up > 1 and down == 1):
-        x = _conv2d_wrapper(x=x, w=w, in_scale=in_scale, **conv)
-        return upfirdn2d.upfirdn2d(x=x, f=f, up=up, padding=[px0, px1, py0, py1], gain=up ** 2, flip_filter=flip_filter)
+        x = _conv2d_wrapper(x=x, w=w, in_scale=in_scale, groups=groups, flip_weight=flip_weight)
+        return tail(upfirdn2d.upfirdn2d(x=x, f=f, up=up, padding=[px0, px1, py0, py1], gain=up ** 2, flip_filter=flip_filter))
 
     # downsampling only: FIR at full resolution, then strided conv
     if down > 1 and up == 1:
@@ -91,7 +121,7 @@ def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight
         x = upfirdn2d.upfirdn2d(x=x, f=f, padding=[px0 + pxt, px1 + pxt, py0 + pyt, py1 + pyt], gain=up ** 2, flip_filter=flip_filter)
         if down > 1:
             x = upfirdn2d.upfirdn2d(x=x, f=f, down=down, flip_filter=flip_filter)
-        return x
+        return tail(x)
 
     # no resampling and a padding the conv kernel takes directly
     if up == 1 and down == 1:
@@ -102,7 +132,7 @@ def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight
     if in_scale is not None:
         x = _fma.scale_nc(x, in_scale)
     x = upfirdn2d.upfirdn2d(x=x, f=(f if up > 1 else None), up=up, padding=[px0, px1, py0, py1], gain=up ** 2, flip_filter=flip_filter)
-    x = _conv2d_wrapper(x=x, w=w, **conv)
     if down > 1:
-        x = upfirdn2d.upfirdn2d(x=x, f=f, down=down, flip_filter=flip_filter)
-    return x
+        x = _conv2d_wrapper(x=x, w=w, groups=groups, flip_weight=flip_weight)
+        return tail(upfirdn2d.upfirdn2d(x=x, f=f, down=down, flip_filter=flip_filter))
+    return _conv2d_wrapper(x=x, w=w, **conv)

@@ -1,0 +1,182 @@
+"""conv2d + the epilogue every StyleGAN2 layer runs after it, as ONE kernel launch forward and (first order) ONE
+activation-sized pass backward:
+
+    y = bias_act( conv2d(x * styles[n,ci], w, stride, padding) * dcoefs[n,co] + noise[n,1,h,w],  b, act, gain, clamp )
+
+This is what `SynthesisLayer.forward` (generators.py:310-329: modulated_conv2d -> fma -> bias_act) and
+`Conv2dLayer.forward` (discriminators.py:115-124: conv2d_resample -> bias_act) compute; the reference spends one
+activation-sized HBM round trip per arrow.  Here the demodulation scale, the noise, the bias, lrelu|linear, the gain
+and the clamp run in the tcgen05 convolution's epilogue while the accumulator leaves TMEM (`sgb_conv_desc.out_scale /
+noise / bias / act`), and the backward of that epilogue is a single pass (`sgb_fused_epilogue_bwd`) that re-derives
+the pre-activation from y.
+
+Gradients of higher order: when the backward itself is being recorded (`create_graph=True`: R1 / path-length
+regularisation) it is evaluated through the un-fused differentiable ops (conv2d_gradfix, fma, bias_act), which is
+exactly the reference's composition.  `conv2d_gradfix.no_weight_gradients()` is honoured on both routes.
+"""
+import torch
+
+from .. import _lib
+from . import bias_act as _ba
+from . import conv2d_gradfix as _cg
+from . import fma as _fma
+
+_ACT_ID = {'linear': 1, 'lrelu': 3}
+# Measured on B200 (ffhq256, batch 32, TF32; profiles/README.md): with the present epilogue the fused forward costs the
+# convolution kernel more than the two activation-sized passes it removes (103.6 ms/step un-fused vs 111.3 fused), so
+# the un-fused composition is the default; `enabled = True` switches the fused kernels on (tests cover both).
+enabled = False
+
+
+def _noise4(noise, n, h, w):
+    if noise is None:
+        return None
+    if noise.ndim < 4 or noise.shape[0] != n:
+        noise = noise.expand(n, 1, h, w)
+    return noise
+
+
+def _unfused(x, w, b, styles, dcoefs, noise, stride, padding, flip_weight, act, alpha, gain, clamp):
+    y = _cg.conv2d(x, w, stride=stride, padding=padding, flip_weight=(not flip_weight), in_scale=styles)
+    if noise is not None:
+        noise = _noise4(noise, y.shape[0], y.shape[2], y.shape[3]).to(y.dtype)
+    if dcoefs is not None:
+        y = _fma.scale_nc(y, dcoefs, noise)
+    elif noise is not None:
+        y = y + noise
+    return _ba.bias_act(y, b, act=act, alpha=alpha, gain=gain, clamp=clamp)
+
+
+def _fusable(x, w, b, styles, dcoefs, noise, act):
+    if not enabled or act not in _ACT_ID or not x.is_cuda or x.ndim != 4 or x.numel() == 0:
+        return False
+    mult = _cg._tc_multiple(x, 1)
+    if not mult or x.shape[1] % mult != 0:
+        return False
+    if not _lib.is_channels_last(x):
+        return False
+    return True
+
+
+def conv2d_bias_act(x, w, b=None, *, stride=1, padding=0, flip_weight=True, styles=None, dcoefs=None, noise=None,
+                    act='linear', alpha=None, gain=None, clamp=None):
+    """See the module docstring.  `flip_weight=True` means correlation (the weight as stored), like conv2d_resample."""
+    spec = _ba.activation_funcs[act]
+    alpha = float(alpha if alpha is not None else spec.def_alpha)
+    gain = float(gain if gain is not None else spec.def_gain)
+    clamp = float(clamp if clamp is not None else -1)
+    padding = tuple(padding) if isinstance(padding, (tuple, list)) else (padding, padding)
+    if not _fusable(x, w, b, styles, dcoefs, noise, act):
+        return _unfused(x, w, b, styles, dcoefs, noise, stride, padding, flip_weight, act, alpha, gain, clamp if clamp >= 0 else None)
+    op = _fused_op(tuple(int(s) for s in w.shape), int(stride), padding, bool(flip_weight), act, alpha, gain, clamp)
+    return op.apply(x, w, b, styles, dcoefs, noise)
+
+
+_cache = dict()
+
+
+def _fused_op(weight_shape, stride, padding, flip_weight, act, alpha, gain, clamp):
+    key = (weight_shape, stride, padding, flip_weight, act, alpha, gain, clamp)
+    if key in _cache:
+        return _cache[key]
+    co, ci, kh, kw = weight_shape
+    flip = not flip_weight
+    conv = _cg._conv2d_op(transpose=False, weight_shape=weight_shape, stride=stride, padding=padding, output_padding=0,
+                          dilation=1, groups=1, flip=flip)
+    clamp_arg = clamp if clamp >= 0 else None
+
+    class FusedConvBiasAct(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, w, b, styles, dcoefs, noise):
+            n = x.shape[0]
+            oh = (x.shape[2] + 2 * padding[0] - kh) // stride + 1
+            ow = (x.shape[3] + 2 * padding[1] - kw) // stride + 1
+            if oh < 1 or ow < 1:
+                raise RuntimeError('conv: output would be empty')
+            if w.dtype != x.dtype:
+                raise RuntimeError('conv: weight and input must have the same dtype')
+            y = torch.empty([n, co, oh, ow], dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+            wc = w.contiguous()
+            sc = _cg._scale_arg(styles, x)
+            d = _cg._make_desc(x, y, False, ci, co, kh, kw, stride, padding, 1, flip, sc, None)
+            acc = _lib.acc_dtype(x.dtype)
+            dc = dcoefs.detach().reshape(n, co).to(acc).contiguous() if dcoefs is not None else None
+            nz = _noise4(noise, n, oh, ow).detach().to(acc).reshape(n, oh, ow).contiguous() if noise is not None else None
+            bb = b.detach().to(x.dtype).contiguous() if b is not None else None
+            d.out_scale, d.noise, d.bias = _lib.ptr(dc), _lib.ptr(nz), _lib.ptr(bb)
+            d.act, d.alpha, d.gain, d.clamp = _ACT_ID[act], alpha, gain, clamp
+            flops = 2.0 * n * oh * ow * co * ci * kh * kw
+            nbytes = (x.numel() + y.numel() + wc.numel()) * x.element_size()
+            ws = _cg._attach_workspace(d, x.device)
+            tc = _lib.lib().sgb_conv2d_uses_tensor_cores(d)
+            with torch.cuda.device(x.device), _lib.prof('conv_fwd_tc' if tc else 'conv_fwd_simt', flops, nbytes):
+                rc = _lib.lib().sgb_conv2d_forward(d, _lib.ptr(x), _lib.ptr(wc), _lib.ptr(y), _lib.stream_ptr(x.device))
+            _lib.check(rc, 'conv2d_forward (fused epilogue)')
+            del ws
+            # y is only kept when the backward depends on it; like the reference (bias_act.py:152-155) a plain linear
+            # epilogue does not, so callers may modify its output in place (`y.add_(x)`, discriminators.py:300)
+            keep_y = act != 'linear' or clamp >= 0 or dcoefs is not None
+            ctx.save_for_backward(x, w, b, styles, dcoefs, noise, y if keep_y else None)
+            ctx.out_shape = tuple(y.shape)
+            return y
+
+        @staticmethod
+        def backward(ctx, dy):
+            x, w, b, styles, dcoefs, noise, y = ctx.saved_tensors
+            need = ctx.needs_input_grad
+            vec = 16 // x.element_size()
+            fast = (not torch.is_grad_enabled()) and co % vec == 0 and co // vec <= 256
+            if not fast:
+                # differentiable route (create_graph=True, or a channel count the one-pass kernel does not take):
+                # the reference's own composition, evaluated on the saved inputs
+                with torch.enable_grad():
+                    y2 = _unfused(x, w, b, styles, dcoefs, noise, stride, padding, flip_weight, act, alpha, gain, clamp_arg)
+                    ins = [t for t, nd in zip((x, w, b, styles, dcoefs, noise), need) if nd and t is not None]
+                    gs = torch.autograd.grad([y2], ins, [dy], create_graph=torch.is_grad_enabled(), allow_unused=True) if ins else []
+                it = iter(gs)
+                return tuple(next(it) if (nd and t is not None) else None
+                             for t, nd in zip((x, w, b, styles, dcoefs, noise), need))
+            n, _, oh, ow = ctx.out_shape
+            dy = dy.contiguous(memory_format=torch.channels_last)
+            dconv = torch.empty_like(dy, memory_format=torch.channels_last)
+            f32 = torch.float32
+            dev = dy.device
+            db = torch.empty([co], dtype=f32, device=dev) if (b is not None and need[2]) else None
+            dsc = torch.empty([n, co], dtype=f32, device=dev) if (dcoefs is not None and need[4]) else None
+            dnz = torch.empty([n, oh, ow], dtype=f32, device=dev) if (noise is not None and need[5]) else None
+            dc = dcoefs.detach().reshape(n, co).to(f32).contiguous() if dcoefs is not None else None
+            nz = _noise4(noise, n, oh, ow).detach().to(f32).reshape(n, oh, ow).contiguous() if noise is not None else None
+            bb = b.detach().to(dy.dtype).contiguous() if b is not None else None
+            with torch.cuda.device(dev), _lib.prof('fused_epilogue_bwd', 0.0, 3 * dy.numel() * dy.element_size()):
+                rc = _lib.lib().sgb_fused_epilogue_bwd(_lib.ptr(dy), _lib.ptr(y), _lib.ptr(dconv), _lib.ptr(bb), _lib.ptr(dc),
+                                                       _lib.ptr(nz), _lib.ptr(db), _lib.ptr(dnz), _lib.ptr(dsc),
+                                                       _lib.dtype_code(dy), n, co, oh * ow, _ACT_ID[act], alpha, gain, clamp,
+                                                       _lib.stream_ptr(dev))
+            _lib.check(rc, 'fused_epilogue_bwd')
+            gx = gw = gs_ = None
+            need_x, need_s = need[0], styles is not None and need[3]
+            if need_x or need_s:
+                pad_out = conv.calc_output_padding(x.shape, dconv.shape)
+                dgrad = _cg._conv2d_op(transpose=True, weight_shape=weight_shape, stride=stride, padding=padding,
+                                       output_padding=pad_out, dilation=1, groups=1, flip=flip)
+                g = dgrad.apply(dconv, w, None, None)
+                if styles is None:
+                    gx = g
+                else:
+                    if need_x:
+                        gx = _fma.scale_nc(g, styles)
+                    if need_s:
+                        gs_ = _fma.mul_sum_hw(g, x).to(styles.dtype)
+            if need[1] and not _cg.weight_gradients_disabled:
+                gw = conv.grad_weight_op.apply(dconv, x, styles)
+            gb = db.to(b.dtype) if db is not None else None
+            gd = dsc.reshape(dcoefs.shape).to(dcoefs.dtype) if dsc is not None else None
+            gn = None
+            if dnz is not None:
+                gn = dnz.reshape(n, 1, oh, ow).to(noise.dtype)
+                if tuple(noise.shape) != (n, 1, oh, ow):       # broadcast noise (noise_mode='const'): un-broadcast
+                    gn = gn.sum_to_size(noise.shape) if noise.ndim == 4 else gn.sum(dim=0).reshape(noise.shape)
+            return gx, gw, gb, gs_, gd, gn
+
+    _cache[key] = FusedConvBiasAct
+    return FusedConvBiasAct
