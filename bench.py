@@ -214,13 +214,15 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         last = None
-        torch.cuda.nvtx.range_push('sgb_timed')           # ncu --nvtx --nvtx-include "sgb_timed/" profiles this loop only
+        nvtx_id = torch.cuda.nvtx.range_start('sgb_timed')   # process-wide range (backward kernels launch from autograd's
+                                                              # thread): ncu --nvtx --nvtx-include "sgb_timed" profiles this loop only
         for _ in range(steps):
             real = host_real.to(device, non_blocking=True) if from_host else dev_real
             out = tr.iteration(real, eager=profile)      # per-launch events need eager launches
             if from_host:
                 last = {k: float(v) for k, v in out.items()}      # D2H read of every loss of the step
-        torch.cuda.nvtx.range_pop()
+        torch.cuda.synchronize(device)
+        torch.cuda.nvtx.range_end(nvtx_id)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
