@@ -291,7 +291,7 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        sb = 2 if R <= 256 else 1
+        sb = 8 if R <= 256 else 1            # ~10-30 s of CPU work on the box's host cores
         v, t = cpu_iteration_rate(cfg, sb)
         cpu = dict(value=v, unit='img/s', cores=torch.get_num_threads(), kind='port',
                    sample=f'Gmain+Dmain+Dreg/{cfg.d_reg_interval}+Greg/{cfg.g_reg_interval} once each at batch {sb}, fp32 '

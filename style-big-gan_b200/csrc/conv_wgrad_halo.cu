@@ -27,6 +27,8 @@ namespace sgb {
 constexpr int WG_THREADS = 160;
 constexpr int WG_LOOKAHEAD = 1;          // tiles in flight per producer thread beyond the one being published
 constexpr int NUM_PRODUCERS_WG = 128;
+constexpr int WS_PRODUCERS = 256;         // fp32 split kernel: 8 producer / converter warps
+constexpr int WS_THREADS = WS_PRODUCERS + 32;
 
 struct WgradHaloParams {
   sgb_conv_desc d;
@@ -264,7 +266,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_halo_kernel(WgradHal
 //   the same thread: LDS its two fp32 chunks of an 8-channel group, (x: multiply by the style), split, STS the bf16
 //   hi / lo chunks into the MMA stage ([hi planes | lo planes] x [chunk of 8 channels][pixel][16 B]), fence, arrive.
 template <int BNC>
-__global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_split_kernel(WgradHaloParams p) {
+__global__ void __launch_bounds__(WS_THREADS, 1) conv_wgrad_split_kernel(WgradHaloParams p) {
   constexpr int KPM = 16;                            // pixels per MMA (bf16: K = 32 bytes)
   constexpr uint32_t IDESC = make_idesc(1, BNC, 1);  // bf16 operands, both MN-major
   constexpr int MAX_STAGES = 4;
@@ -291,10 +293,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_split_kernel(WgradHa
   uint8_t* mma_base = smem + NSTG * p.stage_bytes;
   const int a_half = 16 * p.a_plane, b_half = (BNC / 8) * p.b_plane;
 
-  for (int i = threadIdx.x * 16; i < (NSTG + SA) * p.stage_bytes; i += WG_THREADS * 16) *(uint4*)(smem + i) = make_uint4(0, 0, 0, 0);
-  if (warp == 4) {
+  for (int i = threadIdx.x * 16; i < (NSTG + SA) * p.stage_bytes; i += WS_THREADS * 16) *(uint4*)(smem + i) = make_uint4(0, 0, 0, 0);
+  if (warp == WS_PRODUCERS / 32) {
     if (lane == 0) {
-      for (int i = 0; i < MAX_STAGES; i++) { mbar_init(smem_u32(&full_bar[i]), NUM_PRODUCERS_WG); mbar_init(smem_u32(&empty_bar[i]), 1); }
+      for (int i = 0; i < MAX_STAGES; i++) { mbar_init(smem_u32(&full_bar[i]), WS_PRODUCERS); mbar_init(smem_u32(&empty_bar[i]), 1); }
       mbar_init(smem_u32(&accum_bar), 1);
       fence_barrier_init();
     }
@@ -307,16 +309,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_split_kernel(WgradHa
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
-  if (warp < 4) {
-    // =========================== producers / converters ===========================
+  if (warp < WS_PRODUCERS / 32) {
+    // =========================== producers / converters (8 warps) ===========================
     const int t = threadIdx.x;
     const int cow = (d.co - o0 < UM) ? d.co - o0 : UM;             // valid channels (multiples of 4)
     const int ciw = (d.ci - c0 < BNC) ? d.ci - c0 : BNC;
     const int ga = (cow + 7) / 8, gb = (ciw + 7) / 8;              // 8-channel groups: one thread item = 2 fp32 chunks
     int la = 0; while ((1 << la) < ga) la++;
     int lb = 0; while ((1 << lb) < gb) lb++;
-    const int ja = t & ((1 << la) - 1), pa0 = t >> la, ppa = 128 >> la;
-    const int jb = t & ((1 << lb) - 1), pb0 = t >> lb, ppb = 128 >> lb;
+    const int ja = t & ((1 << la) - 1), pa0 = t >> la, ppa = WS_PRODUCERS >> la;
+    const int jb = t & ((1 << lb) - 1), pb0 = t >> lb, ppb = WS_PRODUCERS >> lb;
     const bool a_two = ja * 8 + 4 < cow, b_two = jb * 8 + 4 < ciw;  // second fp32 chunk of the group exists
     const int npa = p.TH * 8, npb = p.TH * p.HC;
     const int ppb_div = ppb / p.HC, ppb_mod = ppb - ppb_div * p.HC;
@@ -435,8 +437,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_split_kernel(WgradHa
     cp_async_wait<0>();
     while (pub < ntiles) convert_publish(pub++);
 
-    // =========================== epilogue ===========================
-    if (ntiles > 0) {
+    // =========================== epilogue (warps 0-3: one TMEM lane quadrant each) ===========================
+    if (ntiles > 0 && warp < 4) {
       mbar_wait(smem_u32(&accum_bar), 0);
       tc_fence_after();
       const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
@@ -497,7 +499,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_split_kernel(WgradHa
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == WS_PRODUCERS / 32) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
@@ -594,7 +596,7 @@ static int launch_wgrad_split(const sgb_conv_desc* d, const void* x, const void*
     SGB_REQUIRE(e == cudaSuccess, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     attr_set = true;
   }
-  kern<<<dim3((unsigned)otiles, (unsigned)(p.ctiles * d->kh), (unsigned)splits), WG_THREADS, smem, st>>>(p);
+  kern<<<dim3((unsigned)otiles, (unsigned)(p.ctiles * d->kh), (unsigned)splits), WS_THREADS, smem, st>>>(p);
   SGB_LAUNCH_CHECK();
   return 0;
 }
