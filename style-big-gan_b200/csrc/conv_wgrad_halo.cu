@@ -30,6 +30,19 @@ constexpr int NUM_PRODUCERS_WG = 128;
 constexpr int WS_PRODUCERS = 256;         // fp32 split kernel: 8 producer / converter warps
 constexpr int WS_THREADS = WS_PRODUCERS + 32;
 
+__device__ __forceinline__ void cp_async_wait_n(int n) {      // wait until at most n of this thread's groups are pending
+  switch (n) {
+    case 0: cp_async_wait<0>(); break;
+    case 1: cp_async_wait<1>(); break;
+    case 2: cp_async_wait<2>(); break;
+    case 3: cp_async_wait<3>(); break;
+    case 4: cp_async_wait<4>(); break;
+    case 5: cp_async_wait<5>(); break;
+    case 6: cp_async_wait<6>(); break;
+    default: cp_async_wait<7>(); break;
+  }
+}
+
 struct WgradHaloParams {
   sgb_conv_desc d;
   const void* x; const void* dy; float* dw;
@@ -43,6 +56,7 @@ struct WgradHaloParams {
   int a_plane, b_plane;       // bytes between channel chunks
   int a_bytes, stage_bytes;
   int stages;
+  int nstg;                   // fp32 split kernel: staging buffers (tiles in flight from L2 / HBM = nstg - 1)
 };
 
 template <class T, int KIND, int BNC>
@@ -270,7 +284,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_wgrad_split_kernel(WgradHa
   constexpr int KPM = 16;                            // pixels per MMA (bf16: K = 32 bytes)
   constexpr uint32_t IDESC = make_idesc(1, BNC, 1);  // bf16 operands, both MN-major
   constexpr int MAX_STAGES = 4;
-  constexpr int NSTG = WG_LOOKAHEAD + 1;
 
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], accum_bar;
@@ -284,6 +297,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_wgrad_split_kernel(WgradHa
   const int64_t t_end = (t_begin + p.chunk_tiles < p.total_tiles) ? t_begin + p.chunk_tiles : p.total_tiles;
   const int ntiles = t_end > t_begin ? (int)(t_end - t_begin) : 0;
   const int SA = p.stages;
+  const int NSTG = p.nstg, lookahead = p.nstg - 1;
   const int s = d.stride;
   const int o0 = otile * UM, c0 = ctile * BNC;
   const uint32_t tmem_cols = (d.kw * BNC <= 128) ? 128u : ((d.kw * BNC <= 256) ? 256u : 512u);
@@ -330,29 +344,47 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_wgrad_split_kernel(WgradHa
     int pub = 0, sa_p = 0;
     uint32_t ph_p = 0;
 
-    auto tile_origin = [&](int i, int& n, int& oy0, int& ox0) {
-      const int64_t tt = t_begin + i;
-      n = (int)(tt / tiles_per_img);
-      const int rem = (int)(tt - (int64_t)n * tiles_per_img);
+    // tile coordinates advance incrementally (no divisions per tile); one cursor for the loads, one for the conversion
+    struct Cursor { int n, oy0, ox0; };
+    auto cursor_at = [&](int64_t tt) {
+      Cursor c;
+      c.n = (int)(tt / tiles_per_img);
+      const int rem = (int)(tt - (int64_t)c.n * tiles_per_img);
       const int tr = rem / p.col_tiles;
-      oy0 = tr * p.TH; ox0 = (rem - tr * p.col_tiles) * 8;
+      c.oy0 = tr * p.TH; c.ox0 = (rem - tr * p.col_tiles) * 8;
+      return c;
     };
-    // fp32 x8 (two chunks) -> bf16 hi chunk + bf16 lo chunk
+    auto advance = [&](Cursor& c) {
+      c.ox0 += 8;
+      if (c.ox0 >= p.col_tiles * 8) { c.ox0 = 0; c.oy0 += p.TH; if (c.oy0 >= p.row_tiles * p.TH) { c.oy0 = 0; c.n++; } }
+    };
+    Cursor cur_i = cursor_at(t_begin), cur_p = cur_i;
+    // fp32 x8 (two chunks) -> bf16 hi chunk + bf16 lo chunk.  Packed conversions (one F2FP per pair); the bf16 -> fp32
+    // widening needed for the residual is a shift, not a conversion.
     auto split8 = [](const uint4& c0v, const uint4& c1v, const float* sv, uint4& hi, uint4& lo) {
-      const float f[8] = {__uint_as_float(c0v.x), __uint_as_float(c0v.y), __uint_as_float(c0v.z), __uint_as_float(c0v.w),
-                          __uint_as_float(c1v.x), __uint_as_float(c1v.y), __uint_as_float(c1v.z), __uint_as_float(c1v.w)};
-      __nv_bfloat16 h[8], l[8];
+      float f[8] = {__uint_as_float(c0v.x), __uint_as_float(c0v.y), __uint_as_float(c0v.z), __uint_as_float(c0v.w),
+                    __uint_as_float(c1v.x), __uint_as_float(c1v.y), __uint_as_float(c1v.z), __uint_as_float(c1v.w)};
+      if (sv) {
 #pragma unroll
-      for (int e = 0; e < 8; e++) {
-        const float v = sv ? f[e] * sv[e] : f[e];
-        h[e] = __float2bfloat16_rn(v);
-        l[e] = __float2bfloat16_rn(v - __bfloat162float(h[e]));
+        for (int e = 0; e < 8; e++) f[e] *= sv[e];
       }
-      hi = *(const uint4*)h; lo = *(const uint4*)l;
+      uint32_t h[4], l[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const __nv_bfloat162 hp = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+        h[q] = *(const uint32_t*)&hp;
+        const float r0 = f[2 * q] - __uint_as_float(h[q] << 16);
+        const float r1 = f[2 * q + 1] - __uint_as_float(h[q] & 0xffff0000u);
+        const __nv_bfloat162 lp = __floats2bfloat162_rn(r0, r1);
+        l[q] = *(const uint32_t*)&lp;
+      }
+      hi = make_uint4(h[0], h[1], h[2], h[3]); lo = make_uint4(l[0], l[1], l[2], l[3]);
     };
 
+    int stg_p = 0;                                       // staging buffer of the next tile to convert
     auto convert_publish = [&](int i) {                  // tile i has landed in its staging buffer
-      const uint8_t* stg = stg_base + (i % NSTG) * p.stage_bytes;
+      const uint8_t* stg = stg_base + stg_p * p.stage_bytes;
+      if (++stg_p == NSTG) stg_p = 0;
       mbar_wait(smem_u32(&empty_bar[sa_p]), ph_p ^ 1);
       uint8_t* ms = mma_base + sa_p * p.stage_bytes;
       if (ja < ga) {
@@ -369,9 +401,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_wgrad_split_kernel(WgradHa
       if (jb < gb) {
         float sv[8];
         if (scb) {
-          int n, oy0, ox0;
-          tile_origin(i, n, oy0, ox0);
-          const float* sp = scb + (int64_t)n * d.ci + c0 + jb * 8;
+          const float* sp = scb + (int64_t)cur_p.n * d.ci + c0 + jb * 8;
 #pragma unroll
           for (int e = 0; e < 8; e++) sv[e] = (jb * 8 + e < ciw) ? __ldg(sp + e) : 0.f;
         }
@@ -393,12 +423,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_wgrad_split_kernel(WgradHa
       fence_proxy_async();
       mbar_arrive(smem_u32(&full_bar[sa_p]));
       if (++sa_p == SA) { sa_p = 0; ph_p ^= 1; }
+      advance(cur_p);
     };
 
+    int stg_i = 0;                                       // staging buffer of the next tile to load
     for (int i = 0; i < ntiles; i++) {
-      int n, oy0, ox0;
-      tile_origin(i, n, oy0, ox0);
-      const uint32_t a_dst = smem_u32(stg_base + (i % NSTG) * p.stage_bytes);
+      const int n = cur_i.n, oy0 = cur_i.oy0, ox0 = cur_i.ox0;
+      advance(cur_i);
+      const uint32_t a_dst = smem_u32(stg_base + stg_i * p.stage_bytes);
+      if (++stg_i == NSTG) stg_i = 0;
       const uint32_t b_dst = a_dst + 32 * p.a_plane;
       if (ja < ga) {
         const float* src_n = dyb + (int64_t)n * d.y_strides[0] + o0 + ja * 8;
@@ -429,8 +462,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_wgrad_split_kernel(WgradHa
         }
       }
       cp_async_commit();
-      if (i - pub >= WG_LOOKAHEAD) {
-        cp_async_wait<WG_LOOKAHEAD>();
+      if (i - pub >= lookahead) {                          // keep `lookahead` tiles in flight, convert the oldest
+        cp_async_wait_n(lookahead);
         convert_publish(pub++);
       }
     }
@@ -566,18 +599,23 @@ static int launch_wgrad_split(const sgb_conv_desc* d, const void* x, const void*
   p.ctiles = (d->ci + BNC - 1) / BNC;
   const int otiles = (d->co + UM - 1) / UM;
   const int budget = 224 * 1024;
-  const int nstg = WG_LOOKAHEAD + 1;
-  int TH = 8, stages = 0;                               // pixels per tile must be a multiple of 16 (one bf16 MMA): TH >= 2
+  // Tiles are small (their MMAs take ~1 K cycles) and L2 / HBM latency is several K cycles, so the loads of MANY tiles
+  // must be in flight: two MMA stages, every other buffer is fp32 staging; the tile height is the largest that keeps
+  // >= 96 KB in flight (pixels per tile stay a multiple of 16 = one bf16 MMA).
+  int TH = 8, stages = 2, nstg = 2;
   for (;; TH >>= 1) {
     int npa = TH * 8 + 1;
     int npb = TH * p.HC; while (npb % 8 != 1) npb++;
     p.a_plane = npa * 16; p.b_plane = npb * 16;
     p.a_bytes = 32 * p.a_plane;
     p.stage_bytes = (p.a_bytes + (BNC / 4) * p.b_plane + 127) / 128 * 128;     // fp32 staging == bf16 hi + lo planes
-    stages = budget / p.stage_bytes - nstg; if (stages > 4) stages = 4;
-    if (stages >= 3 || TH == 2) break;
+    const int total = budget / p.stage_bytes;
+    nstg = total - stages; if (nstg > 8) nstg = 8;
+    if ((nstg >= 2 && (nstg - 1) * p.stage_bytes >= 96 * 1024) || TH == 2) break;
   }
-  SGB_REQUIRE(stages >= 2, "wgrad split: tile does not fit shared memory");
+  if (nstg < 2) { nstg = 2; }
+  SGB_REQUIRE((nstg + stages) * p.stage_bytes <= budget, "wgrad split: tile does not fit shared memory");
+  p.nstg = nstg;
   p.TH = TH; p.stages = stages;
   p.row_tiles = (d->out_h + TH - 1) / TH; p.col_tiles = (d->out_w + 7) / 8;
   p.total_tiles = (int64_t)d->n * p.row_tiles * p.col_tiles;
