@@ -265,6 +265,11 @@ def main():
     value = args.steps * N * world / (ms / 1000.0)
     # dominant kernel family by device time (eager loop, CUDA events around every libsgb200 launch)
     roof = None
+    traffic = {}
+    tpath = os.path.join(ROOT, 'profiles', 'r1_conv_traffic.json')        # DRAM bytes per launch from ncu (profiles/README.md)
+    if os.path.exists(tpath) and args.workload == 'ffhq256':
+        with open(tpath) as f:
+            traffic = json.load(f)
     if summ:
         total_ms = sum(d['ms'] for d in summ.values()) or 1.0
         dom = max(summ, key=lambda k: summ[k]['ms'])
@@ -274,7 +279,8 @@ def main():
             tf32 = cfg.num_fp16_res == 0 and args.fp32_mode == 'tf32' and dom.startswith('conv_fwd')
             peak = peaks['tc_sustained'] / (2 if tf32 else 1)
             ach = d['flops'] / (d['ms'] / 1000.0) / 1e12
-            roof = dict(kernel=dom, bound='tensor', achieved=ach, peak=peak, unit='TFLOP/s', frac=ach / peak, traffic=None,
+            roof = dict(kernel=dom, bound='tensor', achieved=ach, peak=peak, unit='TFLOP/s', frac=ach / peak,
+                        traffic=(traffic.get(dom) or {}).get('dram_bytes_per_launch'),
                         peak_source=peaks['source'] + (' bf16 sustained / 2 (TF32 MMA rate)' if tf32 else ' bf16 sustained'),
                         launches=d['launches'], avg_launch_ms=d['ms'] / d['launches'], share_of_kernel_time=d['ms'] / total_ms,
                         algorithmic_flops_per_launch=d['flops'] / d['launches'])
