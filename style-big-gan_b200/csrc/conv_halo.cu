@@ -33,7 +33,8 @@ bool conv_halo_eligible(const sgb_conv_desc* d) { return conv_halo_mode(d) >= 0;
 // output-channel tile of the tensor-core kernels for this descriptor (also fixes the packed-weight layout)
 int conv_bn(const sgb_conv_desc* d) {
   const int bn = pick_bn(d->co);
-  if (d->force_simt != 2 && conv_halo_mode(d) == 2 && bn > 128) return 128;   // 4 accumulators must fit 512 TMEM columns
+  static const int m2bn = [] { const char* e = getenv("SGB_HALO_M2BN"); return e ? atoi(e) : 128; }();
+  if (d->force_simt != 2 && conv_halo_mode(d) == 2 && bn > m2bn) return m2bn;   // 4 accumulators must fit 512 TMEM columns
   return bn;
 }
 
@@ -58,6 +59,9 @@ static int pick_gt(const sgb_conv_desc* d, int mode, int bn) {
   while (gt > 1 && !gt_supported(bn, mode, gt)) gt >>= 1;
   if (forced) return gt;
   // keep TMEM double buffering (epilogue overlapped with the next tile's MMAs) unless K is long enough to amortise it
+  static const int m2gt = [] { const char* e = getenv("SGB_HALO_M2GT"); return e ? atoi(e) : 0; }();
+  if (mode == 2 && m2gt) { gt = m2gt; while (gt > 1 && !gt_supported(bn, mode, gt)) gt >>= 1; }
+  else
   while (gt > 1 && nph * gt * bn * 2 > 512 && d->ci < 256) gt >>= 1;
   // do not pad narrow images, keep every SM busy
   while (gt > 1 && (cols % (8 * gt) != 0 ||

@@ -39,7 +39,8 @@
 namespace sgb {
 
 constexpr int TILE_H = 16, TILE_W = 8;
-constexpr int HALO_THREADS = 320;
+constexpr int HALO_PRODUCERS = 256;       // patch producer threads (8 warps)
+constexpr int HALO_THREADS = 192 + HALO_PRODUCERS;
 constexpr int HALO_CH = 4;               // 16-byte channel chunks of K per stage (64 bytes)
 constexpr int MAX_SA = 6, MAX_SB = 8;
 
@@ -79,8 +80,9 @@ __device__ __forceinline__ void cp_async_wait_dyn(int n) {   // wait until at mo
   else cp_async_wait<4>();
 }
 
-constexpr int halo_max_slots(int mode, int gt) {             // ceil(patch pixels * HALO_CH / 128)
-  return mode == 1 ? 18 : (mode == 2 ? (gt == 1 ? 5 : (gt == 2 ? 10 : 18)) : (gt == 1 ? 6 : (gt == 2 ? 11 : 20)));
+constexpr int halo_max_slots(int mode, int gt) {             // ceil(patch pixels * HALO_CH / HALO_PRODUCERS)
+  return (HALO_PRODUCERS == 256) ? (mode == 1 ? 9 : (mode == 2 ? (gt == 1 ? 3 : (gt == 2 ? 5 : 9)) : (gt == 1 ? 3 : (gt == 2 ? 6 : 10))))
+                                 : (mode == 1 ? 18 : (mode == 2 ? (gt == 1 ? 5 : (gt == 2 ? 10 : 18)) : (gt == 1 ? 6 : (gt == 2 ? 11 : 20))));
 }
 
 template <class T, int KIND, int BN, int MODE, int GT>
@@ -97,7 +99,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(HaloParams p
   constexpr uint32_t TMEM_COLS = NEED_COLS <= 32 ? 32 : (NEED_COLS <= 64 ? 64 : (NEED_COLS <= 128 ? 128 : (NEED_COLS <= 256 ? 256 : 512)));
   constexpr uint32_t IDESC = make_idesc(KIND, BN);
   constexpr int MAX_SLOTS = halo_max_slots(MODE, GT);
-  constexpr int PPS = 128 / CH;                       // patch pixels per slot pass
+  constexpr int PPS = HALO_PRODUCERS / CH;            // patch pixels per slot pass
   // epilogue staging: SLAB columns (128 bytes of output per pixel when the tile is that wide)
   constexpr int SLAB = (BN * (int)sizeof(T) >= 128) ? 128 / (int)sizeof(T) : BN;
   constexpr int SLABB = SLAB * (int)sizeof(T);
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(HaloParams p
 
   if (warp == 4) {
     if (lane == 0) {
-      for (int s = 0; s < MAX_SA; s++) { mbar_init(smem_u32(&a_full[s]), 128); mbar_init(smem_u32(&a_empty[s]), 1); }
+      for (int s = 0; s < MAX_SA; s++) { mbar_init(smem_u32(&a_full[s]), HALO_PRODUCERS); mbar_init(smem_u32(&a_empty[s]), 1); }
       for (int s = 0; s < MAX_SB; s++) { mbar_init(smem_u32(&b_full[s]), 1); mbar_init(smem_u32(&b_empty[s]), 1); }
       for (int s = 0; s < 2; s++) { mbar_init(smem_u32(&acc_full[s]), 1); mbar_init(smem_u32(&acc_empty[s]), 4); }
       fence_barrier_init();
@@ -513,7 +515,7 @@ int launch_halo(const sgb_conv_desc* d, const void* x, const void* w, void* y, c
   p.taps = d->kh * d->kw;
   p.cblocks = (d->ci + CH * TC - 1) / (CH * TC);
   int npix = p.HR * p.HC;
-  SGB_REQUIRE(npix * CH <= halo_max_slots(MODE, GT) * 128, "patch too large");
+  SGB_REQUIRE(npix * CH <= halo_max_slots(MODE, GT) * HALO_PRODUCERS, "patch too large");
   while (npix % 8 != 1) npix++;                       // chunk planes 16 B (mod 128 B) apart: conflict-free 128-bit stores
   p.lbo = npix * 16;
   p.a_stage_bytes = (CH * p.lbo + 127) / 128 * 128;
