@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(HaloParams p
 
   if (warp == 4) {
     if (lane == 0) {
-      for (int s = 0; s < MAX_SA; s++) { mbar_init(smem_u32(&a_full[s]), HALO_PRODUCERS); mbar_init(smem_u32(&a_empty[s]), 1); }
+      for (int s = 0; s < MAX_SA; s++) { mbar_init(smem_u32(&a_full[s]), HALO_PRODUCERS / 32); mbar_init(smem_u32(&a_empty[s]), 1); }
       for (int s = 0; s < MAX_SB; s++) { mbar_init(smem_u32(&b_full[s]), 1); mbar_init(smem_u32(&b_empty[s]), 1); }
       for (int s = 0; s < 2; s++) { mbar_init(smem_u32(&acc_full[s]), 1); mbar_init(smem_u32(&acc_empty[s]), 4); }
       fence_barrier_init();
@@ -199,7 +199,8 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(HaloParams p
         }
       }
       fence_proxy_async();
-      mbar_arrive(smem_u32(&a_full[sa]));
+      __syncwarp();                                    // one mbarrier arrival per warp instead of per thread
+      if (lane == 0) mbar_arrive(smem_u32(&a_full[sa]));
       pub++;
       if (++pub_tile_cb == p.cblocks) { pub_tile_cb = 0; pub_tile += gridDim.x; }
     };

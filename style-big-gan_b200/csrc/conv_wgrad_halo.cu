@@ -19,6 +19,7 @@
 //     red.global.add.f32 (dW zeroed by the launcher).
 // Warps 0-3: cp.async producers (+ optional in-place style scaling of the patch), then the epilogue.
 // Warp 4: MMA issuer (one lane), owns TMEM.
+#include <cstdlib>
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_halo_kernel(WgradHal
   for (int i = threadIdx.x * 16; i < SA * p.stage_bytes; i += WG_THREADS * 16) *(uint4*)(smem + i) = make_uint4(0, 0, 0, 0);
   if (warp == 4) {
     if (lane == 0) {
-      for (int i = 0; i < MAX_STAGES; i++) { mbar_init(smem_u32(&full_bar[i]), NUM_PRODUCERS_WG); mbar_init(smem_u32(&empty_bar[i]), 1); }
+      for (int i = 0; i < MAX_STAGES; i++) { mbar_init(smem_u32(&full_bar[i]), NUM_PRODUCERS_WG / 32); mbar_init(smem_u32(&empty_bar[i]), 1); }
       mbar_init(smem_u32(&accum_bar), 1);
       fence_barrier_init();
     }
@@ -156,7 +157,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_halo_kernel(WgradHal
         }
       }
       fence_proxy_async();
-      mbar_arrive(smem_u32(&full_bar[sa]));
+      __syncwarp();                                   // one arrival per warp: 128 serialised arrivals per tile were a fixed cost
+      if (lane == 0) mbar_arrive(smem_u32(&full_bar[sa]));
     };
 
     int sa_i = 0;
@@ -310,7 +312,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_wgrad_split_kernel(WgradHa
   for (int i = threadIdx.x * 16; i < (NSTG + SA) * p.stage_bytes; i += WS_THREADS * 16) *(uint4*)(smem + i) = make_uint4(0, 0, 0, 0);
   if (warp == WS_PRODUCERS / 32) {
     if (lane == 0) {
-      for (int i = 0; i < MAX_STAGES; i++) { mbar_init(smem_u32(&full_bar[i]), WS_PRODUCERS); mbar_init(smem_u32(&empty_bar[i]), 1); }
+      for (int i = 0; i < MAX_STAGES; i++) { mbar_init(smem_u32(&full_bar[i]), WS_PRODUCERS / 32); mbar_init(smem_u32(&empty_bar[i]), 1); }
       mbar_init(smem_u32(&accum_bar), 1);
       fence_barrier_init();
     }
@@ -359,8 +361,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_wgrad_split_kernel(WgradHa
       if (c.ox0 >= p.col_tiles * 8) { c.ox0 = 0; c.oy0 += p.TH; if (c.oy0 >= p.row_tiles * p.TH) { c.oy0 = 0; c.n++; } }
     };
     Cursor cur_i = cursor_at(t_begin), cur_p = cur_i;
-    // fp32 x8 (two chunks) -> bf16 hi chunk + bf16 lo chunk.  Packed conversions (one F2FP per pair); the bf16 -> fp32
-    // widening needed for the residual is a shift, not a conversion.
+    // fp32 x8 (two chunks) -> bf16 hi chunk + bf16 lo chunk, with integer / FADD instructions only (cvt runs on the
+    // slow conversion pipe: it was 12 % of the kernel's stall samples).  hi = the top 16 bits of v (truncation),
+    // lo = the top 16 bits of (v - hi), which is exact in fp32; |v - hi - lo| <= 2^-16 |v|.
     auto split8 = [](const uint4& c0v, const uint4& c1v, const float* sv, uint4& hi, uint4& lo) {
       float f[8] = {__uint_as_float(c0v.x), __uint_as_float(c0v.y), __uint_as_float(c0v.z), __uint_as_float(c0v.w),
                     __uint_as_float(c1v.x), __uint_as_float(c1v.y), __uint_as_float(c1v.z), __uint_as_float(c1v.w)};
@@ -371,12 +374,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_wgrad_split_kernel(WgradHa
       uint32_t h[4], l[4];
 #pragma unroll
       for (int q = 0; q < 4; q++) {
-        const __nv_bfloat162 hp = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
-        h[q] = *(const uint32_t*)&hp;
-        const float r0 = f[2 * q] - __uint_as_float(h[q] << 16);
-        const float r1 = f[2 * q + 1] - __uint_as_float(h[q] & 0xffff0000u);
-        const __nv_bfloat162 lp = __floats2bfloat162_rn(r0, r1);
-        l[q] = *(const uint32_t*)&lp;
+        const uint32_t b0 = __float_as_uint(f[2 * q]), b1 = __float_as_uint(f[2 * q + 1]);
+        h[q] = __byte_perm(b0, b1, 0x7632);                               // {hi16(b1), hi16(b0)}
+        const float r0 = f[2 * q] - __uint_as_float(b0 & 0xffff0000u);
+        const float r1 = f[2 * q + 1] - __uint_as_float(b1 & 0xffff0000u);
+        l[q] = __byte_perm(__float_as_uint(r0), __float_as_uint(r1), 0x7632);
       }
       hi = make_uint4(h[0], h[1], h[2], h[3]); lo = make_uint4(l[0], l[1], l[2], l[3]);
     };
@@ -421,7 +423,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_wgrad_split_kernel(WgradHa
         }
       }
       fence_proxy_async();
-      mbar_arrive(smem_u32(&full_bar[sa_p]));
+      __syncwarp();                                   // one arrival per warp (see above)
+      if (lane == 0) mbar_arrive(smem_u32(&full_bar[sa_p]));
       if (++sa_p == SA) { sa_p = 0; ph_p ^= 1; }
       advance(cur_p);
     };
@@ -602,7 +605,9 @@ static int launch_wgrad_split(const sgb_conv_desc* d, const void* x, const void*
   // Tiles are small (their MMAs take ~1 K cycles) and L2 / HBM latency is several K cycles, so the loads of MANY tiles
   // must be in flight: two MMA stages, every other buffer is fp32 staging; the tile height is the largest that keeps
   // >= 96 KB in flight (pixels per tile stay a multiple of 16 = one bf16 MMA).
-  int TH = 8, stages = 2, nstg = 2;
+  static const int env_sa = [] { const char* e = getenv("SGB_WGRAD_SA"); return e ? atoi(e) : 2; }();
+  static const int env_kb = [] { const char* e = getenv("SGB_WGRAD_KB"); return e ? atoi(e) : 32; }();
+  int TH = 8, stages = env_sa < 2 ? 2 : (env_sa > 4 ? 4 : env_sa), nstg = 2;
   for (;; TH >>= 1) {
     int npa = TH * 8 + 1;
     int npb = TH * p.HC; while (npb % 8 != 1) npb++;
@@ -611,7 +616,7 @@ static int launch_wgrad_split(const sgb_conv_desc* d, const void* x, const void*
     p.stage_bytes = (p.a_bytes + (BNC / 4) * p.b_plane + 127) / 128 * 128;     // fp32 staging == bf16 hi + lo planes
     const int total = budget / p.stage_bytes;
     nstg = total - stages; if (nstg > 8) nstg = 8;
-    if ((nstg >= 2 && (nstg - 1) * p.stage_bytes >= 96 * 1024) || TH == 2) break;
+    if ((nstg >= 2 && (nstg - 1) * p.stage_bytes >= env_kb * 1024) || TH == 2) break;
   }
   if (nstg < 2) { nstg = 2; }
   SGB_REQUIRE((nstg + stages) * p.stage_bytes <= budget, "wgrad split: tile does not fit shared memory");
