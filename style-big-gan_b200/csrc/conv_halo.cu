@@ -41,7 +41,7 @@ int conv_bn(const sgb_conv_desc* d) {
 static bool gt_supported(int bn, int mode, int gt) {
   if (gt == 1) return true;
   if (mode == 1) return false;
-  if (mode == 0) return bn >= 32 && gt * bn <= 512;
+  if (mode == 0) return gt * bn <= 512;
   return bn >= 32 && 4 * gt * bn <= 512;
 }
 

@@ -571,8 +571,8 @@ int dispatch_halo(int bn, int mode, int gt, const sgb_conv_desc* d, const void* 
 #define SGB_HALO_CASE(BN_, MODE_, GT_) \
   if (bn == BN_ && mode == MODE_ && gt == GT_) return launch_halo<T, KIND, BN_, MODE_, GT_>(d, x, w, y, s);
   SGB_HALO_CASE(16, 0, 1) SGB_HALO_CASE(32, 0, 1) SGB_HALO_CASE(64, 0, 1) SGB_HALO_CASE(128, 0, 1) SGB_HALO_CASE(256, 0, 1)
-  SGB_HALO_CASE(32, 0, 2) SGB_HALO_CASE(64, 0, 2) SGB_HALO_CASE(128, 0, 2) SGB_HALO_CASE(256, 0, 2)
-  SGB_HALO_CASE(32, 0, 4) SGB_HALO_CASE(64, 0, 4) SGB_HALO_CASE(128, 0, 4)
+  SGB_HALO_CASE(16, 0, 2) SGB_HALO_CASE(32, 0, 2) SGB_HALO_CASE(64, 0, 2) SGB_HALO_CASE(128, 0, 2) SGB_HALO_CASE(256, 0, 2)
+  SGB_HALO_CASE(16, 0, 4) SGB_HALO_CASE(32, 0, 4) SGB_HALO_CASE(64, 0, 4) SGB_HALO_CASE(128, 0, 4)
   SGB_HALO_CASE(16, 1, 1) SGB_HALO_CASE(32, 1, 1) SGB_HALO_CASE(64, 1, 1) SGB_HALO_CASE(128, 1, 1) SGB_HALO_CASE(256, 1, 1)
   SGB_HALO_CASE(16, 2, 1) SGB_HALO_CASE(32, 2, 1) SGB_HALO_CASE(64, 2, 1) SGB_HALO_CASE(128, 2, 1)
   SGB_HALO_CASE(32, 2, 2) SGB_HALO_CASE(64, 2, 2)
