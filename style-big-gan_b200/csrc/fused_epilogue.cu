@@ -53,27 +53,42 @@ __global__ void __launch_bounds__(256) fused_epilogue_bwd_kernel(FusedBwdParams 
   for (int j = 0; j < VEC; j++) { accb[j] = 0.f; accs[j] = 0.f; }
   const int64_t img = (int64_t)n * p.hw;
   if (active) {
-    for (int px = p0 + pl; px < p1; px += lanes) {
-      const int64_t v = (img + px) * cvt + cv;
-      Vec16<T> dyv, yv, out;
-      dyv.raw = ld_stream((const uint4*)p.dy + v);
-      if (p.y) yv.raw = ld_stream((const uint4*)p.y + v);
-      const float nz = p.noise ? p.noise[img + px] : 0.f;
-      float dn = 0.f;
+    constexpr int U = 4;                                  // pixels in flight per thread (loads issued before the maths)
+    for (int px0 = p0 + pl; px0 < p1; px0 += U * lanes) {
+      Vec16<T> dyv[U], yv[U];
+      float nzv[U];
 #pragma unroll
-      for (int j = 0; j < VEC; j++) {
-        const float yy = p.y ? to_acc<T>(yv.v[j]) : 1.f;       // y not kept (linear, no clamp, no dscale): slope 1, never masked
-        const bool pos = yy > 0.f;
-        float dz = to_acc<T>(dyv.v[j]) * p.gain * (pos ? 1.f : p.alpha);
-        if (clampr >= 0.f && !(yy > -clampr && yy < clampr)) dz = 0.f;
-        const float z = yy * (pos ? inv_g : inv_ga);
-        accb[j] += dz;
-        accs[j] += dz * (z - nz - bs[j]) * inv_sc[j];
-        dn += dz;
-        out.v[j] = from_acc<T>(dz * sc[j]);
+      for (int u = 0; u < U; u++) {
+        const int px = px0 + u * lanes;
+        if (px < p1) {
+          const int64_t v = (img + px) * cvt + cv;
+          dyv[u].raw = ld_stream((const uint4*)p.dy + v);
+          if (p.y) yv[u].raw = ld_stream((const uint4*)p.y + v);
+          nzv[u] = p.noise ? p.noise[img + px] : 0.f;
+        }
       }
-      st_stream((uint4*)p.dconv + v, out.raw);
-      if (p.dnoise) atomicAdd(p.dnoise + img + px, dn);
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int px = px0 + u * lanes;
+        if (px >= p1) break;
+        const int64_t v = (img + px) * cvt + cv;
+        Vec16<T> out;
+        float dn = 0.f;
+#pragma unroll
+        for (int j = 0; j < VEC; j++) {
+          const float yy = p.y ? to_acc<T>(yv[u].v[j]) : 1.f;       // y not kept (linear, no clamp, no dscale): slope 1, never masked
+          const bool pos = yy > 0.f;
+          float dz = to_acc<T>(dyv[u].v[j]) * p.gain * (pos ? 1.f : p.alpha);
+          if (clampr >= 0.f && !(yy > -clampr && yy < clampr)) dz = 0.f;
+          const float z = yy * (pos ? inv_g : inv_ga);
+          accb[j] += dz;
+          accs[j] += dz * (z - nzv[u] - bs[j]) * inv_sc[j];
+          dn += dz;
+          out.v[j] = from_acc<T>(dz * sc[j]);
+        }
+        st_stream((uint4*)p.dconv + v, out.raw);
+        if (p.dnoise) atomicAdd(p.dnoise + img + px, dn);
+      }
     }
   }
   // reduce the per-thread channel sums over the pixel lanes of the block, then one red.add per channel per block

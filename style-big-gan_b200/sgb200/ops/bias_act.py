@@ -71,6 +71,7 @@ def _sum_to_bias(dx, dim):
 
 
 _cache = dict()
+fused_backward = True      # first-order backward: dx and db in one pass (False = the two reference-shaped kernels)
 
 
 def _bias_act_cuda(dim, act, alpha, gain, clamp):
@@ -105,6 +106,25 @@ def _bias_act_cuda(dim, act, alpha, gain, clamp):
         def backward(ctx, dy):
             x, b, y = ctx.saved_tensors
             dx = db = None
+            # first-order fast path (no graph being recorded): dx and db from ONE pass over (dy, y) instead of the
+            # activation-gradient kernel followed by a second read of dx for the bias sum (bias_act.py:172-173)
+            if (fused_backward and not trivial and not torch.is_grad_enabled() and ctx.has_b and ctx.needs_input_grad[1]
+                    and act in ('linear', 'lrelu') and dim == 1 and dy.dim() == 4 and dy.numel() > 0
+                    and dy.dtype in (torch.float32, torch.float16, torch.bfloat16)
+                    and (y is None or _lib.is_channels_last(y)) and (y is not None or _lib.is_channels_last(dy))):
+                vec = 16 // dy.element_size()
+                c = dy.shape[1]
+                if c % vec == 0 and c // vec <= 256 and (y is not None or (act == 'linear' and clamp < 0)):
+                    dyc = dy.contiguous(memory_format=torch.channels_last)
+                    dx = torch.empty_like(dyc, memory_format=torch.channels_last)
+                    dbf = torch.empty([c], dtype=torch.float32, device=dy.device)
+                    n, _, h, w = dy.shape
+                    with torch.cuda.device(dy.device), _lib.prof('bias_act_bwd_fused', 0.0, 3 * dy.numel() * dy.element_size()):
+                        rc = _lib.lib().sgb_fused_epilogue_bwd(_lib.ptr(dyc), _lib.ptr(y), _lib.ptr(dx), None, None, None,
+                                                               _lib.ptr(dbf), None, None, _lib.dtype_code(dy), n, c, h * w,
+                                                               spec.cuda_idx, alpha, gain, clamp, _lib.stream_ptr(dy.device))
+                    _lib.check(rc, 'fused_epilogue_bwd')
+                    return dx, dbf.to(dy.dtype)
             if ctx.needs_input_grad[0] or (ctx.has_b and ctx.needs_input_grad[1]):
                 dx = dy
                 if not trivial:
