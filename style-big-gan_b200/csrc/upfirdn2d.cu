@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(256) upfirdn2d_cl_kernel(UpfirdnParams p, int 
   // first input column any of the PX outputs touches: ceil((ox0*DOWN - padx0) / UP)
   const int bx = ox0 * DOWN - p.padx0;
   const int ix_first = (UP == 1) ? bx : ((bx + PADPAR) >> 1);      // UP == 2: bx has parity PADPAR (ox0 is even)
+  const bool interior = ix_first >= 0 && ix_first + NIX <= p.in_w;
   for (int ty = ty0; ty < FT; ty += UP) {
     const int iy = (base_y + ty) / UP;
     if (iy < 0 || iy >= p.in_h) continue;
@@ -201,10 +202,16 @@ __global__ void __launch_bounds__(256) upfirdn2d_cl_kernel(UpfirdnParams p, int 
     const float frow[4] = {fr.x, fr.y, fr.z, fr.w};
     const T* xr = xn + (int64_t)iy * p.xs[2];
     Vec16<T> in[NIX];
+    if (interior) {                                   // all NIX columns inside the image: no per-load bounds checks
+      const T* xc = xr + (int64_t)ix_first * p.xs[3];
 #pragma unroll
-    for (int i = 0; i < NIX; i++) {
-      const int ix = ix_first + i;
-      in[i].raw = (ix >= 0 && ix < p.in_w) ? __ldg((const uint4*)(xr + (int64_t)ix * p.xs[3])) : make_uint4(0, 0, 0, 0);
+      for (int i = 0; i < NIX; i++) in[i].raw = __ldg((const uint4*)(xc + (int64_t)i * p.xs[3]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < NIX; i++) {
+        const int ix = ix_first + i;
+        in[i].raw = (ix >= 0 && ix < p.in_w) ? __ldg((const uint4*)(xr + (int64_t)ix * p.xs[3])) : make_uint4(0, 0, 0, 0);
+      }
     }
 #pragma unroll
     for (int j = 0; j < PX; j++) {
