@@ -136,6 +136,11 @@ int sgb_fused_epilogue_bwd(const void* dy, const void* y, void* dconv, const voi
                            const void* noise, void* dbias, void* dnoise, void* dscale, int dtype, int n, int c, int hw,
                            int act, float alpha, float gain, float clamp, void* stream);
 
+/* forward of that epilogue as one stand-alone channels_last pass (generators.py:83 fma + :328 bias_act):
+ *   y = clamp(act(x * out_scale[n,c] + noise[n,hw] + bias[c]) * gain);  bias / out_scale / noise may be NULL */
+int sgb_scale_bias_act(const void* x, const void* bias, const void* out_scale, const void* noise, void* y, int dtype,
+                       int n, int c, int hw, int act, float alpha, float gain, float clamp, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -153,3 +153,71 @@ extern "C" int sgb_fused_epilogue_bwd(const void* dy, const void* y, void* dconv
   SGB_LAUNCH_CHECK();
   return 0;
 }
+
+// ---- forward of the same epilogue as a stand-alone pass ----------------------------------------------------------
+//   y = clamp( lrelu|linear( x * out_scale[n,c] + noise[n,h,w] + bias[c] ) * gain )        channels_last, C % VEC == 0
+// One pass instead of the reference's fma (generators.py:83) followed by bias_act (generators.py:328); used for the
+// modulated layers whose convolution is followed by a FIR pass (up-sampling) or whose conv epilogue is not fused.
+namespace sgb {
+struct TailParams {
+  const void* x; void* y; const void* bias; const float* out_scale; const float* noise;
+  int n, c; int64_t hw;
+  float alpha, gain, clamp;
+};
+
+template <class T>
+__global__ void __launch_bounds__(256) scale_bias_act_kernel(TailParams p) {
+  constexpr int VEC = Vec16<T>::N;
+  const int64_t cv = p.c / VEC;
+  const int64_t nv = (int64_t)p.n * p.hw * cv;
+  const float e_clamp = p.clamp >= 0.f ? p.clamp : __int_as_float(0x7f800000);
+  for (int64_t v0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v0 < nv; v0 += (int64_t)gridDim.x * blockDim.x * 2) {
+    const int64_t v1 = v0 + (int64_t)gridDim.x * blockDim.x;
+    Vec16<T> in0, in1;
+    in0.raw = ld_stream((const uint4*)p.x + v0);
+    if (v1 < nv) in1.raw = ld_stream((const uint4*)p.x + v1);
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int64_t v = u ? v1 : v0;
+      if (v >= nv) break;
+      const Vec16<T>& in = u ? in1 : in0;
+      const int64_t pix = v / cv; const int c0 = (int)(v - pix * cv) * VEC; const int64_t n = pix / p.hw;
+      const float nz = p.noise ? p.noise[pix] : 0.f;
+      Vec16<T> out;
+#pragma unroll
+      for (int j = 0; j < VEC; j++) {
+        const float sc = p.out_scale ? __ldg(p.out_scale + n * p.c + c0 + j) : 1.f;
+        const float b = p.bias ? to_acc<T>(((const T*)p.bias)[c0 + j]) : 0.f;
+        float t = fmaf(to_acc<T>(in.v[j]), sc, nz + b);
+        t = fmaxf(t, t * p.alpha) * p.gain;
+        t = fminf(fmaxf(t, -e_clamp), e_clamp);
+        out.v[j] = from_acc<T>(t);
+      }
+      st_stream((uint4*)p.y + v, out.raw);
+    }
+  }
+}
+}  // namespace sgb
+
+extern "C" int sgb_scale_bias_act(const void* x, const void* bias, const void* out_scale, const void* noise, void* y, int dtype,
+                                  int n, int c, int hw, int act, float alpha, float gain, float clamp, void* stream) {
+  SGB_REQUIRE(dtype == SGB_F32 || dtype == SGB_F16 || dtype == SGB_BF16, "unsupported dtype");
+  SGB_REQUIRE(act == SGB_ACT_LINEAR || (act == SGB_ACT_LRELU && alpha <= 1.f), "only linear and lrelu (alpha <= 1) are fused");
+  const int vec = dtype == SGB_F32 ? 4 : 8;
+  SGB_REQUIRE(n >= 0 && c >= 1 && hw >= 0 && c % vec == 0, "channels must be a multiple of one 16-byte vector");
+  if ((int64_t)n * hw == 0) return 0;
+  SGB_REQUIRE(x && y && aligned16(x) && aligned16(y), "x and y must be 16-byte aligned and not NULL");
+  sgb::TailParams p;
+  p.x = x; p.y = y; p.bias = bias; p.out_scale = (const float*)out_scale; p.noise = (const float*)noise;
+  p.n = n; p.c = c; p.hw = hw; p.alpha = (act == SGB_ACT_LINEAR) ? 1.f : alpha; p.gain = gain; p.clamp = clamp;
+  const int64_t nv = (int64_t)n * hw * (c / vec);
+  int64_t blocks = sgb::ceil_div(nv, 512); if (blocks > sgb::kNumSMs * 8) blocks = sgb::kNumSMs * 8;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (dtype) {
+    case SGB_F32:  sgb::scale_bias_act_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(p); break;
+    case SGB_F16:  sgb::scale_bias_act_kernel<__half><<<(unsigned)blocks, 256, 0, s>>>(p); break;
+    default:       sgb::scale_bias_act_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, s>>>(p); break;
+  }
+  SGB_LAUNCH_CHECK();
+  return 0;
+}

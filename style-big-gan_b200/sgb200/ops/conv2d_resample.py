@@ -29,6 +29,10 @@ class Epilogue:
 
     def apply(self, y):
         from . import bias_act
+        if self.dcoefs is not None or self.noise is not None:
+            from . import fused_conv           # demodulation + noise + bias_act as one pass (and a one-pass backward)
+            return fused_conv.scale_bias_act(y, self.b, self.dcoefs, self.noise, act=self.act, alpha=self.alpha, gain=self.gain,
+                                             clamp=self.clamp)
         noise = self.noise
         if noise is not None:
             noise = noise.to(y.dtype)

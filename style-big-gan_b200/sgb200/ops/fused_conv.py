@@ -180,3 +180,96 @@ def _fused_op(weight_shape, stride, padding, flip_weight, act, alpha, gain, clam
 
     _cache[key] = FusedConvBiasAct
     return FusedConvBiasAct
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The same epilogue as ONE stand-alone pass after an un-fused convolution (or after the FIR pass of an up-sampling layer):
+#   y = bias_act(x * dcoefs[n,c] + noise, b, act, gain, clamp)        forward: sgb_scale_bias_act (1 pass instead of 2)
+#   backward (first order): sgb_fused_epilogue_bwd (1 pass instead of bias_act-grad, bias sum, dz * dcoefs, sum(dz * x), sum_c(dz))
+#   backward under create_graph: the reference's composition (fma -> bias_act) on the saved inputs.
+tail_enabled = True
+_tail_cache = dict()
+
+
+def scale_bias_act(x, b, dcoefs, noise, act='linear', alpha=None, gain=None, clamp=None):
+    spec = _ba.activation_funcs[act]
+    alpha = float(alpha if alpha is not None else spec.def_alpha)
+    gain = float(gain if gain is not None else spec.def_gain)
+    clampf = float(clamp if clamp is not None else -1)
+    vec = 16 // x.element_size() if x.dtype in (torch.float32, torch.float16, torch.bfloat16) else 0
+    ok = (tail_enabled and act in _ACT_ID and x.is_cuda and x.ndim == 4 and x.numel() > 0 and vec and x.shape[1] % vec == 0
+          and x.shape[1] // vec <= 256 and _lib.is_channels_last(x) and gain != 0)
+    if not ok:
+        return _tail_unfused(x, b, dcoefs, noise, act, alpha, gain, clamp)
+    key = (act, alpha, gain, clampf)
+    if key not in _tail_cache:
+        _tail_cache[key] = _make_tail(act, alpha, gain, clampf)
+    return _tail_cache[key].apply(x, b, dcoefs, noise)
+
+
+def _tail_unfused(x, b, dcoefs, noise, act, alpha, gain, clamp):
+    if noise is not None:
+        noise = _noise4(noise, x.shape[0], x.shape[2], x.shape[3]).to(x.dtype)
+    if dcoefs is not None:
+        x = _fma.scale_nc(x, dcoefs, noise)
+    elif noise is not None:
+        x = x + noise
+    return _ba.bias_act(x, b, act=act, alpha=alpha, gain=gain, clamp=clamp)
+
+
+def _make_tail(act, alpha, gain, clamp):
+    clamp_arg = clamp if clamp >= 0 else None
+
+    class ScaleBiasAct(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, b, dcoefs, noise):
+            n, c, h, w = x.shape
+            y = torch.empty_like(x, memory_format=torch.channels_last)
+            f32 = torch.float32
+            dc = dcoefs.detach().reshape(n, c).to(f32).contiguous() if dcoefs is not None else None
+            nz = _noise4(noise, n, h, w).detach().to(f32).reshape(n, h, w).contiguous() if noise is not None else None
+            bb = b.detach().to(x.dtype).contiguous() if b is not None else None
+            with torch.cuda.device(x.device), _lib.prof('scale_bias_act', 0.0, 2 * x.numel() * x.element_size()):
+                rc = _lib.lib().sgb_scale_bias_act(_lib.ptr(x), _lib.ptr(bb), _lib.ptr(dc), _lib.ptr(nz), _lib.ptr(y), _lib.dtype_code(x),
+                                                   n, c, h * w, _ACT_ID[act], alpha, gain, clamp, _lib.stream_ptr(x.device))
+            _lib.check(rc, 'scale_bias_act')
+            # x is kept only for the differentiable route (and costs no extra pass); y serves the one-pass backward
+            ctx.save_for_backward(x, b, dcoefs, noise, y)
+            return y
+
+        @staticmethod
+        def backward(ctx, dy):
+            x, b, dcoefs, noise, y = ctx.saved_tensors
+            need = ctx.needs_input_grad
+            if torch.is_grad_enabled():
+                with torch.enable_grad():
+                    y2 = _tail_unfused(x, b, dcoefs, noise, act, alpha, gain, clamp_arg)
+                    ins = [t for t, nd in zip((x, b, dcoefs, noise), need) if nd and t is not None]
+                    gs = torch.autograd.grad([y2], ins, [dy], create_graph=True, allow_unused=True) if ins else []
+                it = iter(gs)
+                return tuple(next(it) if (nd and t is not None) else None for t, nd in zip((x, b, dcoefs, noise), need))
+            n, c, h, w = y.shape
+            dy = dy.contiguous(memory_format=torch.channels_last)
+            dx = torch.empty_like(y, memory_format=torch.channels_last)
+            f32, dev = torch.float32, y.device
+            db = torch.empty([c], dtype=f32, device=dev) if (b is not None and need[1]) else None
+            dsc = torch.empty([n, c], dtype=f32, device=dev) if (dcoefs is not None and need[2]) else None
+            dnz = torch.empty([n, h, w], dtype=f32, device=dev) if (noise is not None and need[3]) else None
+            dc = dcoefs.detach().reshape(n, c).to(f32).contiguous() if dcoefs is not None else None
+            nz = _noise4(noise, n, h, w).detach().to(f32).reshape(n, h, w).contiguous() if noise is not None else None
+            bb = b.detach().to(y.dtype).contiguous() if b is not None else None
+            with torch.cuda.device(dev), _lib.prof('fused_epilogue_bwd', 0.0, 3 * y.numel() * y.element_size()):
+                rc = _lib.lib().sgb_fused_epilogue_bwd(_lib.ptr(dy), _lib.ptr(y), _lib.ptr(dx), _lib.ptr(bb), _lib.ptr(dc), _lib.ptr(nz),
+                                                       _lib.ptr(db), _lib.ptr(dnz), _lib.ptr(dsc), _lib.dtype_code(y), n, c, h * w,
+                                                       _ACT_ID[act], alpha, gain, clamp, _lib.stream_ptr(dev))
+            _lib.check(rc, 'fused_epilogue_bwd')
+            gb = db.to(b.dtype) if db is not None else None
+            gd = dsc.reshape(dcoefs.shape).to(dcoefs.dtype) if dsc is not None else None
+            gn = None
+            if dnz is not None:
+                gn = dnz.reshape(n, 1, h, w).to(noise.dtype)
+                if tuple(noise.shape) != (n, 1, h, w):
+                    gn = gn.sum_to_size(noise.shape) if noise.ndim == 4 else gn.sum(dim=0).reshape(noise.shape)
+            return (dx if need[0] else None), gb, gd, gn
+
+    return ScaleBiasAct

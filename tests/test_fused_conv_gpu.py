@@ -163,3 +163,46 @@ def test_fused_conv_honours_no_weight_gradients():
     finally:
         fused_conv.enabled = False
     assert gw is None and gx is not None
+
+
+@pytest.mark.parametrize('dtype', [torch.float16, torch.float32])
+@pytest.mark.parametrize('clamp', [None, 0.8])
+def test_scale_bias_act_tail_matches_unfused(dtype, clamp):
+    """One-pass demodulation + noise + bias_act (and its one-pass backward) vs the fma -> bias_act composition."""
+    from sgb200.ops import fused_conv
+    g = torch.Generator().manual_seed(4)
+    n, c, h = 3, 32, 12
+    x = torch.randn(n, c, h, h, generator=g)
+    b = torch.randn(c, generator=g) * 0.3
+    d = torch.rand(n, c, generator=g) + 0.5
+    nz = torch.randn(n, 1, h, h, generator=g) * 0.2
+    dy = torch.randn(n, c, h, h, generator=g)
+
+    def run(on):
+        fused_conv.tail_enabled = on
+        try:
+            lx = _cl(x.to(DEV, dtype)).requires_grad_(True)
+            lb = b.to(DEV, dtype).requires_grad_(True)
+            ld = d.to(DEV).requires_grad_(True)
+            ln = nz.to(DEV).requires_grad_(True)
+            y = fused_conv.scale_bias_act(lx, lb, ld, ln, act='lrelu', gain=math.sqrt(2), clamp=clamp)
+            gs = torch.autograd.grad(y, [lx, lb, ld, ln], _cl(dy.to(DEV, dtype)))
+            return y, gs
+        finally:
+            fused_conv.tail_enabled = True
+
+    yf, gf = run(True)
+    yu, gu = run(False)
+    # fp16: the un-fused route rounds x * dcoefs + noise to fp16 before bias_act, so elements within rounding distance of
+    # the lrelu / clamp breakpoints take the other branch (see _l2_close); a saturating clamp puts many elements there
+    tol = (6e-2 if clamp is not None else 2e-2) if dtype == torch.float16 else 1e-4
+    assert_close(yf, yu.float().cpu(), 2e-3 if dtype == torch.float16 else 1e-5, f'y {dtype}')
+    for nm, a, u in zip('x b dcoefs noise'.split(), gf, gu):
+        _l2_close(a, u, tol, f'd{nm} {dtype} clamp={clamp}')
+    # second order through the differentiable route
+    lx = _cl(x.to(DEV, dtype)).requires_grad_(True)
+    ld = d.to(DEV).requires_grad_(True)
+    y = fused_conv.scale_bias_act(lx, b.to(DEV, dtype), ld, nz.to(DEV), act='lrelu', gain=math.sqrt(2), clamp=clamp)
+    gx, = torch.autograd.grad(y.float().square().sum(), [lx], create_graph=True)
+    gd, = torch.autograd.grad(gx.float().square().sum(), [ld])
+    assert torch.isfinite(gd).all() and gd.abs().max() > 0
