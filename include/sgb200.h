@@ -141,6 +141,11 @@ int sgb_fused_epilogue_bwd(const void* dy, const void* y, void* dconv, const voi
 int sgb_scale_bias_act(const void* x, const void* bias, const void* out_scale, const void* noise, void* y, int dtype,
                        int n, int c, int hw, int act, float alpha, float gain, float clamp, void* stream);
 
+/* backward of the fused style modulation (sgb_conv_desc.in_scale) in one channels_last pass: gx = g * s[n,c] (dtype of g),
+ * gs[n,c] = sum_hw g * x (fp32, overwritten).  gx or gs may be NULL.  Replaces the two passes over g of the reference's
+ * `x * styles` backward (generators.py:80). */
+int sgb_mod_bwd(const void* g, const void* x, const void* s, void* gx, void* gs, int dtype, int n, int c, int hw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

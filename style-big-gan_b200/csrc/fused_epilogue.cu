@@ -221,3 +221,100 @@ extern "C" int sgb_scale_bias_act(const void* x, const void* bias, const void* o
   SGB_LAUNCH_CHECK();
   return 0;
 }
+
+// ---- backward of the fused style modulation (conv in_scale) in one pass -------------------------------------------
+//   gx[n,c,h,w] = g * s[n,c]           (gradient wrt the un-modulated activations)
+//   gs[n,c]     = sum_hw g * x         (gradient wrt the styles)
+// g = data gradient of the convolution wrt (x * s).  The reference reads g twice (generators.py:80 backward: mul by
+// styles, and the un-broadcast sum of g * x); channels_last, C % VEC == 0, C / VEC <= 256.
+namespace sgb {
+struct ModBwdParams { const void* g; const void* x; const float* s; void* gx; float* gs; int n, c, hw, ppb, blocks_per_img; };
+
+template <class T>
+__global__ void __launch_bounds__(256) mod_bwd_kernel(ModBwdParams p) {
+  constexpr int VEC = Vec16<T>::N;
+  __shared__ float red[256];
+  const int cvt = p.c / VEC, lanes = 256 / cvt;
+  const int cv = threadIdx.x % cvt, pl = threadIdx.x / cvt;
+  const int n = blockIdx.x / p.blocks_per_img;
+  const int p0 = (blockIdx.x - n * p.blocks_per_img) * p.ppb;
+  const int p1 = (p0 + p.ppb < p.hw) ? p0 + p.ppb : p.hw;
+  const bool active = pl < lanes;
+  const int c0 = cv * VEC;
+  float sc[VEC], acc[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; j++) { sc[j] = p.s[(int64_t)n * p.c + c0 + j]; acc[j] = 0.f; }
+  const int64_t img = (int64_t)n * p.hw;
+  if (active) {
+    constexpr int U = 4;
+    for (int px0 = p0 + pl; px0 < p1; px0 += U * lanes) {
+      Vec16<T> gv[U], xv[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int px = px0 + u * lanes;
+        if (px < p1) {
+          const int64_t v = (img + px) * cvt + cv;
+          gv[u].raw = ld_stream((const uint4*)p.g + v);
+          if (p.gs) xv[u].raw = ld_stream((const uint4*)p.x + v);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int px = px0 + u * lanes;
+        if (px >= p1) break;
+        const int64_t v = (img + px) * cvt + cv;
+        Vec16<T> out;
+#pragma unroll
+        for (int j = 0; j < VEC; j++) {
+          const float gg = to_acc<T>(gv[u].v[j]);
+          if (p.gs) acc[j] += gg * to_acc<T>(xv[u].v[j]);
+          out.v[j] = from_acc<T>(gg * sc[j]);
+        }
+        if (p.gx) st_stream((uint4*)p.gx + v, out.raw);
+      }
+    }
+  }
+  if (p.gs) {
+#pragma unroll
+    for (int j = 0; j < VEC; j++) {
+      __syncthreads();
+      red[threadIdx.x] = active ? acc[j] : 0.f;
+      __syncthreads();
+      if (pl == 0) {
+        float t = 0.f;
+        for (int l = 0; l < lanes; l++) t += red[l * cvt + cv];
+        atomicAdd(p.gs + (int64_t)n * p.c + c0 + j, t);
+      }
+    }
+  }
+}
+}  // namespace sgb
+
+extern "C" int sgb_mod_bwd(const void* g, const void* x, const void* s, void* gx, void* gs, int dtype, int n, int c, int hw, void* stream) {
+  SGB_REQUIRE(dtype == SGB_F32 || dtype == SGB_F16 || dtype == SGB_BF16, "unsupported dtype");
+  const int vec = dtype == SGB_F32 ? 4 : 8;
+  SGB_REQUIRE(n >= 0 && c >= 1 && hw >= 0 && c % vec == 0 && c / vec <= 256, "channels must be a multiple of one 16-byte vector (at most 256 vectors)");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (gs) SGB_REQUIRE(cudaMemsetAsync(gs, 0, sizeof(float) * (size_t)n * c, st) == cudaSuccess, "memset failed");
+  if ((int64_t)n * hw == 0) return 0;
+  SGB_REQUIRE(g && s && (gx || gs) && (x || !gs), "g, s and at least one output must not be NULL");
+  SGB_REQUIRE(aligned16(g) && aligned16(x) && aligned16(gx), "tensors must be 16-byte aligned");
+  sgb::ModBwdParams p;
+  p.g = g; p.x = x; p.s = (const float*)s; p.gx = gx; p.gs = (float*)gs; p.n = n; p.c = c; p.hw = hw;
+  const int cvt = c / vec, lanes = 256 / cvt;
+  int64_t want = ((int64_t)sgb::kNumSMs * 4 + n - 1) / n;
+  int64_t maxb = ((int64_t)hw + lanes - 1) / lanes;
+  if (want > maxb) want = maxb;
+  if (want < 1) want = 1;
+  p.ppb = (int)(((int64_t)hw + want - 1) / want);
+  p.blocks_per_img = (hw + p.ppb - 1) / p.ppb;
+  const int64_t grid = (int64_t)n * p.blocks_per_img;
+  SGB_REQUIRE(grid <= 0x7fffffff, "grid too large");
+  switch (dtype) {
+    case SGB_F32:  sgb::mod_bwd_kernel<float><<<(unsigned)grid, 256, 0, st>>>(p); break;
+    case SGB_F16:  sgb::mod_bwd_kernel<__half><<<(unsigned)grid, 256, 0, st>>>(p); break;
+    default:       sgb::mod_bwd_kernel<__nv_bfloat16><<<(unsigned)grid, 256, 0, st>>>(p); break;
+  }
+  SGB_LAUNCH_CHECK();
+  return 0;
+}

@@ -129,6 +129,28 @@ def _scale_arg(in_scale, x):
     return in_scale.detach().to(_lib.acc_dtype(x.dtype)).contiguous()
 
 
+def _modulation_backward(g, x, in_scale, need_x, need_s):
+    """gradients of y = conv(x * s) wrt x and s from g = d(x * s): one pass (sgb_mod_bwd) when no graph is being recorded,
+    else the two differentiable ops of fma.py"""
+    from . import fma as _fma
+    vec = 16 // g.element_size() if g.dtype in (torch.float32, torch.float16, torch.bfloat16) else 0
+    c = g.shape[1]
+    if (not torch.is_grad_enabled() and vec and c % vec == 0 and c // vec <= 256 and g.numel() > 0
+            and _lib.is_channels_last(g) and _lib.is_channels_last(x)):
+        n, _, h, w = g.shape
+        gx = torch.empty_like(g, memory_format=torch.channels_last) if need_x else None
+        gs = torch.empty([n, c], dtype=torch.float32, device=g.device) if need_s else None
+        s32 = in_scale.detach().to(torch.float32).contiguous()
+        with torch.cuda.device(g.device), _lib.prof('mod_bwd', 0.0, 3 * g.numel() * g.element_size()):
+            rc = _lib.lib().sgb_mod_bwd(_lib.ptr(g), _lib.ptr(x), _lib.ptr(s32), _lib.ptr(gx), _lib.ptr(gs), _lib.dtype_code(g),
+                                        n, c, h * w, _lib.stream_ptr(g.device))
+        _lib.check(rc, 'mod_bwd')
+        return gx, (gs.to(in_scale.dtype) if gs is not None else None)
+    gx = _fma.scale_nc(g, in_scale) if need_x else None
+    gs = _fma.mul_sum_hw(g, x).to(in_scale.dtype) if need_s else None
+    return gx, gs
+
+
 _cache = dict()
 
 
@@ -224,11 +246,7 @@ def _conv2d_op(transpose, weight_shape, stride, padding, output_padding, dilatio
                 if in_scale is None:
                     grad_input = g
                 else:
-                    from . import fma as _fma
-                    if need_x:
-                        grad_input = _fma.scale_nc(g, in_scale)
-                    if need_s:
-                        grad_scale = _fma.mul_sum_hw(g, input).to(in_scale.dtype)
+                    grad_input, grad_scale = _modulation_backward(g, input, in_scale, need_x, need_s)
             if ctx.needs_input_grad[1] and not weight_gradients_disabled:
                 grad_weight = Conv2dGradWeight.apply(grad_output, input, in_scale)
                 assert tuple(grad_weight.shape) == weight_shape
