@@ -110,7 +110,9 @@ int sgb_conv2d_wgrad(const sgb_conv_desc* d, const void* x, const void* dy, void
 /* 1 if the tcgen05 (tensor-core) implicit-GEMM path will be used for this descriptor, 0 if the
  * generic SIMT kernel; for reporting only. */
 int sgb_conv2d_uses_tensor_cores(const sgb_conv_desc* d);
-/* same question for sgb_conv2d_wgrad */
+/* same question for sgb_conv2d_wgrad: 0 = SIMT, non-zero = tensor cores; 2 = the halo-tile kernels, the only ones that
+ * accept d->out_scale in a weight-gradient descriptor (there it is a per-sample scale [N, co] on dy: the style modulation
+ * of a transposed convolution, whose input plays the role of dy). */
 int sgb_conv2d_wgrad_uses_tensor_cores(const sgb_conv_desc* d);
 
 /* ---- modulation helpers (activation-sized passes of modulated_conv2d, generators.py:80-87; fma.py) ----

@@ -43,8 +43,9 @@ static int wgrad_route(const sgb_conv_desc* d) {
   return d->dtype == SGB_F32 ? 0 : 1;
 }
 
+// 0 = SIMT; non-zero = tensor cores, 2 = the halo-tile kernels (the ones that also take out_scale = a scale on dy)
 extern "C" int sgb_conv2d_wgrad_uses_tensor_cores(const sgb_conv_desc* d) {
-  return (d && !d->transposed && wgrad_route(d) != 0) ? 1 : 0;
+  return (d && !d->transposed) ? wgrad_route(d) : 0;
 }
 
 extern "C" int sgb_conv2d_uses_tensor_cores(const sgb_conv_desc* d) {
@@ -68,6 +69,7 @@ extern "C" int sgb_conv2d_wgrad(const sgb_conv_desc* d, const void* x, const voi
   SGB_REQUIRE(!d->transposed, "wgrad takes the non-transposed description (swap x and dy for conv_transpose2d)");
   SGB_REQUIRE(dw, "dw must not be NULL");
   SGB_REQUIRE((x && dy) || (int64_t)d->n == 0, "x and dy must not be NULL");
+  SGB_REQUIRE(!d->out_scale || wgrad_route(d) == 2, "wgrad: out_scale (a scale on dy) is only taken by the halo-tile kernels");
   switch (wgrad_route(d)) {
     case 2: return conv_wgrad_halo(d, x, dy, dw, (cudaStream_t)stream);
     case 1: return conv_wgrad_umma(d, x, dy, dw, (cudaStream_t)stream);

@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_halo_kernel(WgradHal
     const T* xb = (const T*)p.x;
     const T* dyb = (const T*)p.dy;
     const float* scb = (const float*)d.in_scale;
+    const float* sca = (const float*)d.out_scale;                  // per-sample scale of the dy channels
     const int tiles_per_img = p.row_tiles * p.col_tiles;
     int pub = 0;
 
@@ -154,6 +155,29 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_halo_kernel(WgradHal
           *q = v;
           hr += ppb_div; hc += ppb_mod;
           if (hc >= p.HC) { hc -= p.HC; hr++; }
+        }
+      }
+      if (sca && ja < cpa) {                                        // same for the dy tile (out_scale)
+        int n, oy0, ox0;
+        tile_origin(i, n, oy0, ox0);
+        const float* sp = sca + (int64_t)n * d.co + o0 + ja * TC;
+        float sv[TC];
+#pragma unroll
+        for (int e = 0; e < TC; e += 4) { const float4 q = __ldg((const float4*)(sp + e)); sv[e] = q.x; sv[e + 1] = q.y; sv[e + 2] = q.z; sv[e + 3] = q.w; }
+        uint8_t* adst = smem + sa * p.stage_bytes + ja * p.a_plane;
+        for (int pp = pa0; pp < npa; pp += ppa) {
+          uint4* q = (uint4*)(adst + pp * 16);
+          uint4 v = *q;
+          if (KIND == 2) {
+            float* f = (float*)&v;
+#pragma unroll
+            for (int e = 0; e < 4; e++) f[e] *= sv[e % TC];
+          } else {
+            T* h = (T*)&v;
+#pragma unroll
+            for (int e = 0; e < TC; e++) h[e] = from_acc<T>(to_acc<T>(h[e]) * sv[e]);
+          }
+          *q = v;
         }
       }
       fence_proxy_async();
@@ -342,6 +366,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_wgrad_split_kernel(WgradHa
     const float* xb = (const float*)p.x;
     const float* dyb = (const float*)p.dy;
     const float* scb = (const float*)d.in_scale;
+    const float* sca = (const float*)d.out_scale;                  // per-sample scale of the dy channels
     const int tiles_per_img = p.row_tiles * p.col_tiles;
     int pub = 0, sa_p = 0;
     uint32_t ph_p = 0;
@@ -390,12 +415,18 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_wgrad_split_kernel(WgradHa
       mbar_wait(smem_u32(&empty_bar[sa_p]), ph_p ^ 1);
       uint8_t* ms = mma_base + sa_p * p.stage_bytes;
       if (ja < ga) {
+        float sv[8];
+        if (sca) {
+          const float* sp = sca + (int64_t)cur_p.n * d.co + o0 + ja * 8;
+#pragma unroll
+          for (int e = 0; e < 8; e++) sv[e] = (ja * 8 + e < cow) ? __ldg(sp + e) : 0.f;
+        }
         const uint8_t* src = stg + (2 * ja) * p.a_plane;
         uint8_t* dst = ms + ja * p.a_plane;
         for (int pp = pa0; pp < npa; pp += ppa) {
           const uint4 c0v = *(const uint4*)(src + pp * 16), c1v = *(const uint4*)(src + p.a_plane + pp * 16);
           uint4 hi, lo;
-          split8(c0v, c1v, nullptr, hi, lo);
+          split8(c0v, c1v, sca ? sv : nullptr, hi, lo);
           *(uint4*)(dst + pp * 16) = hi;
           *(uint4*)(dst + a_half + pp * 16) = lo;
         }

@@ -263,10 +263,19 @@ def _conv2d_op(transpose, weight_shape, stride, padding, output_padding, dilatio
                 x_, dy_, sc = input, grad_output, _scale_arg(in_scale, input)
                 d = _make_desc(x_, dy_, False, ci, co, kh, kw, s, padding, groups, flip, sc)
             else:
-                if in_scale is not None:
-                    raise NotImplementedError('in_scale with conv_transpose2d weight gradients: scale the input explicitly')
-                x_, dy_ = grad_output, input
+                # the op's input plays the role of dy: its style scale goes into the descriptor's out_scale (taken by
+                # the halo-tile kernels only; otherwise the input is scaled explicitly first)
+                x_, dy_, sc = grad_output, input, None
                 d = _make_desc(x_, dy_, False, co, ci, kh, kw, s, padding, groups, flip)
+                if in_scale is not None:
+                    mult_ = _tc_multiple(input, groups)
+                    if _lib.lib().sgb_conv2d_wgrad_uses_tensor_cores(d) == 2 and not (mult_ and (ci % mult_ or co % mult_)):
+                        sc_dy = _scale_arg(in_scale, input)
+                        d.out_scale = _lib.ptr(sc_dy)
+                    else:
+                        from . import fma as _fma
+                        dy_ = _fma.scale_nc(input.detach(), in_scale.detach())
+                        d = _make_desc(x_, dy_, False, co, ci, kh, kw, s, padding, groups, flip)
             flops = 2.0 * dy_.shape[0] * dy_.shape[2] * dy_.shape[3] * dy_.shape[1] * (x_.shape[1] // groups) * kh * kw
             nbytes = (x_.numel() + dy_.numel()) * x_.element_size()
             # dw has the layout of the weight of the NON-transposed conv x_ -> dy_: [C(dy_), C(x_)/groups, kh, kw]

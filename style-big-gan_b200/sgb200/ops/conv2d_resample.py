@@ -55,9 +55,6 @@ def _conv2d_wrapper(x, w, stride=1, padding=0, groups=1, transpose=False, flip_w
                                               dcoefs=e.dcoefs, noise=e.noise, act=e.act, alpha=e.alpha, gain=e.gain, clamp=e.clamp)
         return epilogue.apply(_conv2d_wrapper(x, w, stride, padding, groups, transpose, flip_weight, in_scale))
     op = conv2d_gradfix.conv_transpose2d if transpose else conv2d_gradfix.conv2d
-    if transpose and in_scale is not None:      # the transposed kernel's weight gradient has no fused scale
-        x = _fma.scale_nc(x, in_scale)
-        in_scale = None
     return op(x, w, stride=stride, padding=padding, groups=groups, flip_weight=(not flip_weight), in_scale=in_scale)
 
 

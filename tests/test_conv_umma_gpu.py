@@ -199,7 +199,7 @@ def test_halo_conv_vs_oracle_and_v1(dtype, case):
     s = (torch.randn(n, ci) + 1).to(DEV)
     op = cg.conv_transpose2d if tr else cg.conv2d
     fo = torch.nn.functional.conv_transpose2d if tr else torch.nn.functional.conv2d
-    for scale in ((None, s) if not tr else (None,)):
+    for scale in (None, s):
         xo = x.cpu().float() * (1 if scale is None else scale.cpu()[:, :, None, None])
         yo = fo(xo, w.cpu().float(), stride=stride, padding=pad)
         for gt in (0, 1, 2, 4):          # tiles per super-tile: automatic, then forced (falls back to what TMEM allows)
@@ -255,3 +255,49 @@ def test_channel_padding_makes_small_channel_convs_tensor_core(dtype, case):
     assert_close(y, yo, TOL, f'{case} {dtype} y')
     assert_close(dx, dxo, TOL, f'{case} {dtype} dx')
     assert_close(dw, dwo, TOL, f'{case} {dtype} dw')
+
+
+@pytest.mark.parametrize('dtype', [torch.float16, torch.float32])
+@pytest.mark.parametrize('case', [
+    # (N, Ci, Co, H, W, pad, stride, tensor_cores)
+    (2, 128, 64, 16, 16, 0, 2, True),        # G up path: conv_transpose2d stride 2
+    (3, 72, 40, 7, 11, 0, 2, True),          # odd sizes, channel tails
+    (2, 64, 64, 12, 12, 1, 1, True),         # stride-1 transposed (dgrad form)
+    (2, 10, 6, 9, 9, 0, 2, True),            # channel counts that need zero padding: the scale is applied explicitly
+    (2, 64, 32, 8, 8, 0, 2, False),          # SIMT route
+])
+def test_transposed_conv_in_scale_gradients(dtype, case):
+    """conv_transpose2d(x * s[n,c]) with the style scale fused into the op: forward, gradients wrt x, w and s against the
+    CPU oracle; the weight gradient takes the scale on its dy operand (descriptor out_scale) on the halo-tile route."""
+    from sgb200.ops import conv2d_gradfix as cg
+    from sgb200 import _lib
+    n, ci, co, h, wd, pad, stride, tc = case
+    torch.manual_seed(31)
+    torch.backends.cudnn.allow_tf32 = True
+    x = _cl(torch.randn(n, ci, h, wd).to(DEV, dtype)).requires_grad_(True)
+    w = (torch.randn(ci, co, 3, 3) / math.sqrt(ci * 9)).to(DEV, dtype).requires_grad_(True)
+    s = (torch.randn(n, ci) + 1).to(DEV, dtype).requires_grad_(True)
+    cg.use_tensor_cores = tc
+    try:
+        _lib.profile_start()
+        y = cg.conv_transpose2d(x, w, stride=stride, padding=pad, in_scale=s)
+        dy = _cl(torch.randn(y.shape).to(DEV, dtype))
+        dx, dw, ds = torch.autograd.grad(y, [x, w, s], dy)
+        torch.cuda.synchronize()
+        kinds = set(_lib.profile_stop().summary())
+    finally:
+        cg.use_tensor_cores = True
+    if tc:
+        assert 'conv_wgrad_tc' in kinds and 'conv_fwd_simt' not in kinds, kinds
+        if ci % 8 == 0 and co % 8 == 0:
+            assert 'scale_nc' not in kinds, kinds            # the scale rode inside the kernels
+    xo = x.detach().cpu().float().requires_grad_(True)
+    wo = w.detach().cpu().float().requires_grad_(True)
+    so = s.detach().cpu().float().requires_grad_(True)
+    yo = torch.nn.functional.conv_transpose2d(xo * so[:, :, None, None], wo, stride=stride, padding=pad)
+    dxo, dwo, dso = torch.autograd.grad(yo, [xo, wo, so], dy.cpu().float())
+    tol = TOL if tc else 2e-3
+    assert_close(y, yo.detach(), tol, f'{case} {dtype} y')
+    assert_close(dx, dxo, tol, f'{case} {dtype} dx')
+    assert_close(dw, dwo, tol, f'{case} {dtype} dw')
+    assert_close(ds, dso, tol, f'{case} {dtype} ds')
