@@ -25,24 +25,13 @@
 
 namespace sgb {
 
+int conv_wgrad_tf32(const sgb_conv_desc* d, const void* x, const void* dy, float* dw, cudaStream_t s);   // conv_wgrad_tf32.cu
+
 constexpr int WG_THREADS = 160;
 constexpr int WG_LOOKAHEAD = 1;          // tiles in flight per producer thread beyond the one being published
 constexpr int NUM_PRODUCERS_WG = 128;
 constexpr int WS_PRODUCERS = 256;         // fp32 split kernel: 8 producer / converter warps
 constexpr int WS_THREADS = WS_PRODUCERS + 32;
-
-__device__ __forceinline__ void cp_async_wait_n(int n) {      // wait until at most n of this thread's groups are pending
-  switch (n) {
-    case 0: cp_async_wait<0>(); break;
-    case 1: cp_async_wait<1>(); break;
-    case 2: cp_async_wait<2>(); break;
-    case 3: cp_async_wait<3>(); break;
-    case 4: cp_async_wait<4>(); break;
-    case 5: cp_async_wait<5>(); break;
-    case 6: cp_async_wait<6>(); break;
-    default: cp_async_wait<7>(); break;
-  }
-}
 
 struct WgradHaloParams {
   sgb_conv_desc d;
@@ -327,11 +316,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_wgrad_split_kernel(WgradHa
   const int s = d.stride;
   const int o0 = otile * UM, c0 = ctile * BNC;
   const uint32_t tmem_cols = (d.kw * BNC <= 128) ? 128u : ((d.kw * BNC <= 256) ? 256u : 512u);
-  // staging: fp32 layout [chunk of 4 channels][pixel][16 B] with the same plane strides (32 + BNC/4 planes);
-  // MMA stage: [A hi: 16 planes][A lo: 16][B hi: BNC/8][B lo: BNC/8], plane = (pixels padded) * 16 B
+  // staging: fp32 layout [chunk of 4 channels][pixel][16 B] with the same plane strides (PA + BNC/4 planes, PA = 32, or
+  // 16 when dy has <= 64 channels); MMA stage: [A hi: PA/2 planes][A lo: PA/2][B hi: BNC/8][B lo: BNC/8],
+  // plane = (pixels padded) * 16 B
   uint8_t* stg_base = smem;
   uint8_t* mma_base = smem + NSTG * p.stage_bytes;
-  const int a_half = 16 * p.a_plane, b_half = (BNC / 8) * p.b_plane;
+  const int a_half = p.a_bytes / 2, b_half = (BNC / 8) * p.b_plane;
 
   for (int i = threadIdx.x * 16; i < (NSTG + SA) * p.stage_bytes; i += WS_THREADS * 16) *(uint4*)(smem + i) = make_uint4(0, 0, 0, 0);
   if (warp == WS_PRODUCERS / 32) {
@@ -438,7 +428,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_wgrad_split_kernel(WgradHa
 #pragma unroll
           for (int e = 0; e < 8; e++) sv[e] = (jb * 8 + e < ciw) ? __ldg(sp + e) : 0.f;
         }
-        const uint8_t* src = stg + 32 * p.a_plane + (2 * jb) * p.b_plane;
+        const uint8_t* src = stg + p.a_bytes + (2 * jb) * p.b_plane;
         uint8_t* dst = ms + 2 * a_half + jb * p.b_plane;
         int hr = pb0_r, hc = pb0_c;
         for (int hp = pb0; hp < npb; hp += ppb) {
@@ -466,7 +456,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_wgrad_split_kernel(WgradHa
       advance(cur_i);
       const uint32_t a_dst = smem_u32(stg_base + stg_i * p.stage_bytes);
       if (++stg_i == NSTG) stg_i = 0;
-      const uint32_t b_dst = a_dst + 32 * p.a_plane;
+      const uint32_t b_dst = a_dst + p.a_bytes;
       if (ja < ga) {
         const float* src_n = dyb + (int64_t)n * d.y_strides[0] + o0 + ja * 8;
         const uint32_t dst_j = a_dst + (2 * ja) * p.a_plane;
@@ -643,7 +633,9 @@ static int launch_wgrad_split(const sgb_conv_desc* d, const void* x, const void*
     int npa = TH * 8 + 1;
     int npb = TH * p.HC; while (npb % 8 != 1) npb++;
     p.a_plane = npa * 16; p.b_plane = npb * 16;
-    p.a_bytes = 32 * p.a_plane;
+    // <= 64 dy channels: half the A planes.  The M = 128 MMA still reads 16 planes per half; what it finds beyond the
+    // valid ones (the lo half, the x planes -- all inside the stage) only reaches accumulator rows that are never stored
+    p.a_bytes = (d->co <= 64 ? 16 : 32) * p.a_plane;
     p.stage_bytes = (p.a_bytes + (BNC / 4) * p.b_plane + 127) / 128 * 128;     // fp32 staging == bf16 hi + lo planes
     const int total = budget / p.stage_bytes;
     nstg = total - stages; if (nstg > 8) nstg = 8;
@@ -689,7 +681,10 @@ int conv_wgrad_halo(const sgb_conv_desc* d, const void* x, const void* dy, void*
   if ((int64_t)d->n * d->out_h * d->out_w == 0) return 0;
   if (d->dtype == SGB_F16) return dispatch_wgrad_halo<__half, 0>(d, x, dy, (float*)dw, s);
   if (d->dtype == SGB_BF16) return dispatch_wgrad_halo<__nv_bfloat16, 1>(d, x, dy, (float*)dw, s);
-  // fp32: kind::tf32 does not take MN-major operands in this layout -> 3 x bf16 split kernel
+  // fp32: kind::tf32 takes MN-major operands only in the SWIZZLE_128B_BASE32B layout (conv_wgrad_tf32.cu); the earlier
+  // 3 x bf16 split kernel (fp32-exact products, ~1.7x slower) stays selectable with SGB_WGRAD_FP32=split
+  static const bool use_split = [] { const char* e = getenv("SGB_WGRAD_FP32"); return e && std::string(e) == "split"; }();
+  if (!use_split) return conv_wgrad_tf32(d, x, dy, (float*)dw, s);
   if (d->ci <= 32) return launch_wgrad_split<32>(d, x, dy, (float*)dw, s);
   if (d->ci <= 64) return launch_wgrad_split<64>(d, x, dy, (float*)dw, s);
   return launch_wgrad_split<128>(d, x, dy, (float*)dw, s);
