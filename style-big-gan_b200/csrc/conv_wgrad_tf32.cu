@@ -286,7 +286,7 @@ static int launch_wgrad_tf32(const sgb_conv_desc* d, const void* x, const void* 
   // last two alias the x patch (inside the stage as long as it is at least as large), and only reach accumulator rows
   // that are never stored.
   const int PA = (d->co <= 64 && BNC >= 64) ? 2 : 4;
-  int TH = (env_th == 2 || env_th == 4 || env_th == 8 || env_th == 16) ? env_th : 8, stages = 0;
+  int TH = (env_th == 2 || env_th == 4 || env_th == 8 || env_th == 16 || env_th == 32) ? env_th : 16, stages = 0;
   for (;; TH >>= 1) {
     p.a_blk = TH * 8 * 128;
     p.b_blk = (TH * p.HC + 3) / 4 * 4 * 128;
