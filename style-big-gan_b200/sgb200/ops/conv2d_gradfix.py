@@ -224,7 +224,7 @@ def _conv2d_op(transpose, weight_shape, stride, padding, output_padding, dilatio
                 nbytes = (input.numel() + y.numel() + w.numel()) * input.element_size()
                 ws = _attach_workspace(d, input.device)
                 tc = _lib.lib().sgb_conv2d_uses_tensor_cores(d)
-                with torch.cuda.device(input.device), _lib.prof('conv_fwd_tc' if tc else 'conv_fwd_simt', flops, nbytes):
+                with torch.cuda.device(input.device), _lib.prof(('conv_fwd_simt', 'conv_fwd_tc', 'conv_fwd_small')[tc], flops, nbytes):
                     rc = _lib.lib().sgb_conv2d_forward(d, _lib.ptr(x_), _lib.ptr(w), _lib.ptr(y), _lib.stream_ptr(input.device))
                 _lib.check(rc, 'conv2d_forward')
             ctx.save_for_backward(input, weight, in_scale)

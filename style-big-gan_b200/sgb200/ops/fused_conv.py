@@ -14,6 +14,8 @@ Gradients of higher order: when the backward itself is being recorded (`create_g
 regularisation) it is evaluated through the un-fused differentiable ops (conv2d_gradfix, fma, bias_act), which is
 exactly the reference's composition.  `conv2d_gradfix.no_weight_gradients()` is honoured on both routes.
 """
+import os
+
 import torch
 
 from .. import _lib
@@ -25,7 +27,7 @@ _ACT_ID = {'linear': 1, 'lrelu': 3}
 # Measured on B200 (ffhq256, batch 32, TF32; profiles/README.md): with the present epilogue the fused forward costs the
 # convolution kernel more than the two activation-sized passes it removes (103.6 ms/step un-fused vs 111.3 fused), so
 # the un-fused composition is the default; `enabled = True` switches the fused kernels on (tests cover both).
-enabled = False
+enabled = os.environ.get('SGB_FUSED_CONV', '0') == '1'
 
 
 def _noise4(noise, n, h, w):

@@ -301,3 +301,43 @@ def test_transposed_conv_in_scale_gradients(dtype, case):
     assert_close(dx, dxo, tol, f'{case} {dtype} dx')
     assert_close(dw, dwo, tol, f'{case} {dtype} dw')
     assert_close(ds, dso, tol, f'{case} {dtype} ds')
+
+
+@pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16, torch.float32])
+@pytest.mark.parametrize('case', [
+    # (N, Ci, Co, H, W, transposed)
+    (3, 64, 3, 32, 32, False),          # toRGB
+    (2, 128, 3, 17, 23, False),         # odd sizes: partial last block
+    (2, 64, 3, 16, 16, True),           # data gradient of fromRGB
+    (2, 32, 8, 9, 9, False),            # the 8-accumulator instantiation
+    (1, 512, 1, 4, 4, False),
+])
+def test_small_co_1x1_kernel(dtype, case):
+    """1x1 convolutions with <= 8 output channels run the bandwidth kernel (conv_small.cu), style scale included;
+    forward and all three gradients against the CPU oracle."""
+    from sgb200.ops import conv2d_gradfix as cg
+    from sgb200 import _lib
+    n, ci, co, h, wd, tr = case
+    torch.manual_seed(41)
+    torch.backends.cudnn.allow_tf32 = True
+    x = _cl(torch.randn(n, ci, h, wd).to(DEV, dtype)).requires_grad_(True)
+    w = (torch.randn((ci, co, 1, 1) if tr else (co, ci, 1, 1)) / math.sqrt(ci)).to(DEV, dtype).requires_grad_(True)
+    s = (torch.randn(n, ci) + 1).to(DEV, dtype).requires_grad_(True)
+    op = cg.conv_transpose2d if tr else cg.conv2d
+    fo = torch.nn.functional.conv_transpose2d if tr else torch.nn.functional.conv2d
+    for scale in (None, s):
+        _lib.profile_start()
+        y = op(x, w, in_scale=scale)
+        torch.cuda.synchronize()
+        assert set(_lib.profile_stop().summary()) == {'conv_fwd_small'}
+        dy = _cl(torch.randn(y.shape).to(DEV, dtype))
+        ins = [x, w] + ([scale] if scale is not None else [])
+        grads = torch.autograd.grad(y, ins, dy)
+        xo = x.detach().cpu().float().requires_grad_(True)
+        wo = w.detach().cpu().float().requires_grad_(True)
+        so = s.detach().cpu().float().requires_grad_(True)
+        yo = fo(xo * so[:, :, None, None] if scale is not None else xo, wo)
+        gos = torch.autograd.grad(yo, [xo, wo] + ([so] if scale is not None else []), dy.cpu().float())
+        assert_close(y, yo.detach(), TOL, f'{case} {dtype} y scale={scale is not None}')
+        for g, go, name in zip(grads, gos, ('dx', 'dw', 'ds')):
+            assert_close(g, go, TOL, f'{case} {dtype} {name} scale={scale is not None}')
