@@ -47,7 +47,7 @@ constexpr int MAX_SA = 6, MAX_SB = 8;
 struct HaloParams {
   sgb_conv_desc d;
   const void* x; const void* wpack; void* y;
-  int VR;               // rows of the tile-row space per image (MODE 0: out_h + kh - 1; else padded to 16)
+  int VR;               // rows of the tile-row space per image (MODE 0: out_h + kh - 1; MODE 2: in_h + 1; MODE 1: out_h padded to 16)
   int HR, HC;           // patch rows / column slots per row
   int QP;               // MODE 1: slot offset of the odd-column plane
   int top, left;        // patch origin relative to the tile origin (input coordinates)
@@ -178,7 +178,8 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(HaloParams p
             if (hrc[i] >= 0) {
               int n = n0;
               if (MODE == 0) { int r = rem0 + (hrc[i] >> 16); while (r >= p.VR) { r -= p.VR; n++; } }
-              n = n < d.n ? n : d.n - 1;
+              if (MODE == 2) { int r = rem0 - p.top + (hrc[i] >> 16); if (r < 0) n--; while (r >= p.VR) { r -= p.VR; n++; } }
+              n = n < d.n ? (n < 0 ? 0 : n) : d.n - 1;
               const float* sp = scb + (int64_t)n * d.ci + co;
               uint4* q = (uint4*)(dst + dsl[i]);
               uint4 v = *q;
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(HaloParams p
 #pragma unroll
         for (int i = 0; i < MAX_SLOTS; i++) off[i] = -1;
       } else {
-        const int n0 = u0 / p.VR, r0 = u0 - n0 * p.VR;             // MODE 1 / 2: tiles never straddle images
+        const int n0 = u0 / p.VR, r0 = u0 - n0 * p.VR;             // MODE 1: tiles never straddle images
 #pragma unroll
         for (int i = 0; i < MAX_SLOTS; i++) {
           off[i] = -1;
@@ -229,9 +230,12 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(HaloParams p
             } else if (MODE == 1) {
               iy = 2 * r0 - p.top + hr; ix = 2 * x0 - p.left + hc;
             } else {
-              iy = r0 - p.top + hr; ix = x0 - p.left + hc;
+              int r = r0 - p.top + hr;
+              if (r < 0) { r += p.VR; n--; }
+              while (r >= p.VR) { r -= p.VR; n++; }
+              iy = r; ix = x0 - p.left + hc;
             }
-            if (n < d.n && iy >= 0 && iy < d.in_h && ix >= 0 && ix < d.in_w)
+            if (n >= 0 && n < d.n && iy >= 0 && iy < d.in_h && ix >= 0 && ix < d.in_w)
               off[i] = (int)(n * d.x_strides[0] + iy * d.x_strides[2] + ix * d.x_strides[3]);
           }
         }
@@ -374,7 +378,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(HaloParams p
         auto out_pixel = [&](int mm, int& n, int& oy, int& ox) -> bool {
           int r = r0 + (mm >> 3);
           n = n0;
-          if (MODE == 0) { while (r >= p.VR) { r -= p.VR; n++; } }
+          if (MODE != 1) { while (r >= p.VR) { r -= p.VR; n++; } }
           const int cx = x0 + g * TILE_W + (mm & 7);
           if (MODE == 2) { oy = 2 * r + py - d.pad_y; ox = 2 * cx + px - d.pad_x; }
           else { oy = r; ox = cx; }
@@ -493,8 +497,10 @@ int launch_halo(const sgb_conv_desc* d, const void* x, const void* w, void* y, c
   } else {
     p.top = (d->kh - 1) >> 1; p.left = (d->kw - 1) >> 1;
     p.HR = TILE_H + p.top; p.HC = TW + p.left;
+    // virtual rows per image (tiles straddle images as in MODE 0): the last one is an all-zero input row, so that the
+    // patch row it shares with the next image's row -1 is zero for both
     const int rows_img = ((d->out_h - 1 + d->pad_y) >> 1) + 1;
-    p.VR = (rows_img + TILE_H - 1) / TILE_H * TILE_H;
+    p.VR = rows_img > d->in_h + 1 ? rows_img : d->in_h + 1;
     p.col_tiles = ((((d->out_w - 1 + d->pad_x) >> 1) + 1) + TW - 1) / TW;
   }
   for (int tap = 0; tap < d->kh * d->kw; tap++) {
@@ -510,7 +516,7 @@ int launch_halo(const sgb_conv_desc* d, const void* x, const void* w, void* y, c
       p.tap_acc[tap] = (ky & 1) * 2 + (kx & 1);
     }
   }
-  const int64_t row_tiles = (MODE == 0) ? ceil_div((int64_t)d->n * p.VR, TILE_H) : (int64_t)d->n * (p.VR / TILE_H);
+  const int64_t row_tiles = (MODE != 1) ? ceil_div((int64_t)d->n * p.VR, TILE_H) : (int64_t)d->n * (p.VR / TILE_H);
   p.ntiles = (d->co + BN - 1) / BN;
   p.total_tiles = row_tiles * p.col_tiles * p.ntiles;
   p.taps = d->kh * d->kw;
