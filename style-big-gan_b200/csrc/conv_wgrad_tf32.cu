@@ -43,6 +43,7 @@ struct WgradTf32Params {
   int a_blk, b_blk;           // bytes per 32-channel block (rows * 128, multiples of 512)
   int a_bytes, stage_bytes;
   int stages, lookahead;
+  int stack;                  // 1: the kw taps of a 32-channel block are one MMA (N = 96, LBO = one patch row)
 };
 
 // byte offset of 16-byte chunk c (0..7) inside row `row` of a block whose base is 512-byte aligned
@@ -218,7 +219,8 @@ __global__ void __launch_bounds__(WT_THREADS, 1) conv_wgrad_tf32_kernel(WgradTf3
 #pragma unroll 1
         for (int cc = 0; cc < BNC; cc += 16) {
           uint32_t acc[16];
-          tmem_ld16(lane_addr + kx * BNC + cc, acc);
+          // accumulator columns: [tap][channel], or per 32-channel block [tap][32 channels] when the taps are stacked in N
+          tmem_ld16(lane_addr + (p.stack ? (cc >> 5) * 96 + kx * 32 + (cc & 31) : kx * BNC + cc), acc);
           if (o >= d.co) continue;
 #pragma unroll
           for (int e = 0; e < 16; e++) {
@@ -244,7 +246,21 @@ __global__ void __launch_bounds__(WT_THREADS, 1) conv_wgrad_tf32_kernel(WgradTf3
         mbar_wait(smem_u32(&full_bar[sa]), pha);
         tc_fence_after();
         const uint32_t a_lo0 = a_lo_base + sa * stage_u, b_lo0 = b_lo_base + sa * stage_u;
-        if (lane == 0) {
+        if (lane == 0 && p.stack) {
+          // stride 1, three taps: tap kx of a 32-channel block is the same block one patch row further down, i.e. the
+          // next N block of a descriptor whose LBO is one row (128 B).  One N = 96 MMA per block and tile row reads
+          // the dy tile once for the three taps instead of three times.
+          constexpr uint32_t IDESC96 = make_idesc(2, 96, 1);
+          const uint32_t bs_lo0 = smem_desc_lo(smem_u32(smem) + (uint32_t)p.a_bytes, 128) + sa * stage_u;
+          for (int cbk = 0; cbk < BNC / 32; cbk++) {
+            const uint32_t b_lo = bs_lo0 + cbk * ((uint32_t)p.b_blk >> 4);
+            const uint32_t tm = tmem_base + cbk * 96;
+#pragma unroll 4
+            for (int ty = 0; ty < p.TH; ty++)
+              umma_lh<2>(tm, a_lo0 + ty * 64, hi, b_lo + ty * b_row_u, hi, IDESC96, (i > 0 || ty > 0) ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&empty_bar[sa]));
+        } else if (lane == 0) {
           for (int kx = 0; kx < d.kw; kx++) {
             const uint32_t b_lo = b_lo0 + (uint32_t)(((kx % s) * p.QP + kx / s) * 8);
             const uint32_t tm = tmem_base + kx * BNC;
@@ -278,6 +294,8 @@ static int launch_wgrad_tf32(const sgb_conv_desc* d, const void* x, const void* 
   p.HC = 7 * s + d->kw;
   p.QP = (s == 1) ? 0 : (p.HC + 1) / 2;
   p.ctiles = (d->ci + BNC - 1) / BNC;
+  static const int env_stack = [] { const char* e = getenv("SGB_WGRAD_STACK"); return e ? atoi(e) : 1; }();
+  p.stack = (env_stack && s == 1 && d->kw == 3 && BNC <= 64) ? 1 : 0;
   const int otiles = (d->co + UM - 1) / UM;
   const int budget = 224 * 1024;
   static const int env_th = [] { const char* e = getenv("SGB_WGRAD_TH"); return e ? atoi(e) : 0; }();
