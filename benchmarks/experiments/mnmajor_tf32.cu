@@ -14,7 +14,7 @@
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__global__ void __launch_bounds__(128) k(const float* Ag, const float* Bg, float* D, int K, int shift, int bmode, int variant, int KB_rows) {
+__global__ void __launch_bounds__(128) k(const float* Ag, const float* Bg, float* D, int K, int shift, int bmode, int variant, int KB_rows, int m64) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar;
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(128) k(const float* Ag, const float* Bg, float
   const uint32_t tmem = tslot;
   if (tid == 0) {
     // idesc: fp32 accum (1<<4), a/b = tf32 (2<<7, 2<<10), a_major/b_major = MN (1<<15, 1<<16), N>>3 at 17, M>>4 at 24
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | (((m64 ? 64u : 128u) >> 4) << 24);
     for (int kk = 0; kk < K / 8; kk++) {
       const uint32_t a_start = smem_u32(sa) + kk * 8 * 128;
       const uint32_t b_start = smem_u32(sb) + (shift + kk * 8) * 128;
@@ -100,11 +100,28 @@ int main(int argc, char** argv) {
   cudaMalloc(&dA, A.size() * 4); cudaMalloc(&dB, B.size() * 4); cudaMalloc(&dD, 128 * 64 * 4);
   cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice); cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  k<<<1, 128, 100 * 1024>>>(dA, dB, dD, K, shift, bmode, variant, KB_rows);
+  const int m64 = argc > 4 ? atoi(argv[4]) : 0;
+  cudaMemset(dD, 0xff, 128 * 64 * 4);
+  k<<<1, 128, 100 * 1024>>>(dA, dB, dD, K, shift, bmode, variant, KB_rows, m64);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
   std::vector<float> D(128 * 64);
   cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
+  if (m64) {      // M = 64: which TMEM lane holds which row of D?
+    for (int m = 0; m < 64; m++) {
+      int found = -1;
+      for (int l = 0; l < 128 && found < 0; l++) {
+        bool ok = true;
+        for (int n = 0; n < 64 && ok; n++) {
+          double r = 0; for (int kk = 0; kk < K; kk++) r += (double)Af[kk * 128 + m] * Bf[(kk + shift) * 64 + n];
+          ok = fabs(r - D[l * 64 + n]) < 1e-3;
+        }
+        if (ok) found = l;
+      }
+      printf("row %d -> lane %d\n", m, found);
+    }
+    return 0;
+  }
   double maxerr = 0, maxref = 0;
   for (int m = 0; m < 128; m++) for (int n = 0; n < 64; n++) {
     double r = 0; for (int kk = 0; kk < K; kk++) r += (double)Af[kk * 128 + m] * Bf[(kk + shift) * 64 + n];
