@@ -43,6 +43,7 @@ struct WgradTf32Params {
   int a_blk, b_blk;           // bytes per 32-channel block (rows * 128, multiples of 512)
   int a_bytes, stage_bytes;
   int stages, lookahead;
+  int m64;                    // 1: <= 64 dy channels, M = 64 MMAs (accumulator row r sits in TMEM lane (r % 16) + 32 * (r / 16))
   int stack;                  // 1: the kw taps of a 32-channel block are one MMA (N = 96, LBO = one patch row)
 };
 
@@ -53,7 +54,8 @@ __device__ __forceinline__ uint32_t swz_row(int row, int c) {
 
 template <int BNC>
 __global__ void __launch_bounds__(WT_THREADS, 1) conv_wgrad_tf32_kernel(WgradTf32Params p) {
-  constexpr uint32_t IDESC = make_idesc(2, BNC, 1);  // tf32 operands, both MN-major
+  // instruction descriptor: fp32 accumulate, tf32 operands, both MN-major, N >> 3 at [17,23), M >> 4 at [24,29)
+  auto idesc_of = [](uint32_t m, uint32_t n) { return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((n >> 3) << 17) | ((m >> 4) << 24); };
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // the swizzle is a function of the absolute address: blocks must start on 512-byte boundaries (1 KB of slack is allocated)
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) conv_wgrad_tf32_kernel(WgradTf3
       mbar_wait(smem_u32(&accum_bar), 0);
       tc_fence_after();
       const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-      const int o = o0 + threadIdx.x;
+      const int o = p.m64 ? ((lane < 16) ? o0 + warp * 16 + lane : d.co) : o0 + threadIdx.x;
       const int wy = d.flip ? d.kh - 1 - ky : ky;
       for (int kx = 0; kx < d.kw; kx++) {
         const int wx = d.flip ? d.kw - 1 - kx : kx;
@@ -235,6 +237,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) conv_wgrad_tf32_kernel(WgradTf3
     // =========================== MMA issuer ===========================
     // whole warp runs the loop (uniform values), lane 0 issues; descriptors as (lo, hi) halves, ring counters
     {
+      const uint32_t IDESC = idesc_of(p.m64 ? 64u : 128u, (uint32_t)BNC);
       const uint32_t hi = smem_desc_hi(512) | (1u << 29);                     // SBO = 4 rows; layout type 1 (bits 61-63)
       const uint32_t a_lo_base = smem_desc_lo(smem_u32(smem), (uint32_t)p.a_blk);
       const uint32_t b_lo_base = smem_desc_lo(smem_u32(smem) + (uint32_t)p.a_bytes, (uint32_t)p.b_blk);
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) conv_wgrad_tf32_kernel(WgradTf3
           // stride 1, three taps: tap kx of a 32-channel block is the same block one patch row further down, i.e. the
           // next N block of a descriptor whose LBO is one row (128 B).  One N = 96 MMA per block and tile row reads
           // the dy tile once for the three taps instead of three times.
-          constexpr uint32_t IDESC96 = make_idesc(2, 96, 1);
+          const uint32_t IDESC96 = idesc_of(p.m64 ? 64u : 128u, 96u);
           const uint32_t bs_lo0 = smem_desc_lo(smem_u32(smem) + (uint32_t)p.a_bytes, 128) + sa * stage_u;
           for (int cbk = 0; cbk < BNC / 32; cbk++) {
             const uint32_t b_lo = bs_lo0 + cbk * ((uint32_t)p.b_blk >> 4);
@@ -300,10 +303,12 @@ static int launch_wgrad_tf32(const sgb_conv_desc* d, const void* x, const void* 
   const int budget = 224 * 1024;
   static const int env_th = [] { const char* e = getenv("SGB_WGRAD_TH"); return e ? atoi(e) : 0; }();
   static const int env_la = [] { const char* e = getenv("SGB_WGRAD_LA"); return e ? atoi(e) : 0; }();
-  // <= 64 dy channels: two 32-channel blocks instead of four.  The M = 128 MMA still reads four blocks LBO apart; the
-  // last two alias the x patch (inside the stage as long as it is at least as large), and only reach accumulator rows
-  // that are never stored.
-  const int PA = (d->co <= 64 && BNC >= 64) ? 2 : 4;
+  // <= 64 dy channels: two 32-channel blocks and M = 64 MMAs (half the shared-memory reads of the dy operand)
+  static const int env_m64 = [] { const char* e = getenv("SGB_WGRAD_M64"); return e ? atoi(e) : 1; }();
+  p.m64 = (env_m64 && d->co <= 64) ? 1 : 0;
+  // without M = 64 the M = 128 MMA reads four blocks LBO apart: the last two alias the x patch (inside the stage as long
+  // as it is at least as large) and only reach accumulator rows that are never stored
+  const int PA = (d->co <= 64 && (p.m64 || BNC >= 64)) ? 2 : 4;
   int TH = (env_th == 2 || env_th == 4 || env_th == 8 || env_th == 16 || env_th == 32) ? env_th : 16, stages = 0;
   for (;; TH >>= 1) {
     p.a_blk = TH * 8 * 128;
