@@ -64,7 +64,8 @@ static int pick_gt(const sgb_conv_desc* d, int mode, int bn) {
   else
   while (gt > 1 && nph * gt * bn * 2 > 512 && d->ci < 256) gt >>= 1;
   // do not pad narrow images, keep every SM busy
-  while (gt > 1 && (cols % (8 * gt) != 0 ||
+  const bool keep_cols = (mode == 2 && m2gt);      // experiment: accept the padded last column tile
+  while (gt > 1 && ((!keep_cols && cols % (8 * gt) != 0) ||
                     ceil_div((int64_t)d->n * rows, 16) * ceil_div(cols, 8 * gt) * ntiles < kNumSMs)) gt >>= 1;
   return gt;
 }
