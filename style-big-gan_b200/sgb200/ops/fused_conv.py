@@ -25,8 +25,9 @@ from . import fma as _fma
 
 _ACT_ID = {'linear': 1, 'lrelu': 3}
 # Measured on B200 (ffhq256, batch 32, TF32; profiles/README.md): with the present epilogue the fused forward costs the
-# convolution kernel more than the two activation-sized passes it removes (103.6 ms/step un-fused vs 111.3 fused), so
-# the un-fused composition is the default; `enabled = True` switches the fused kernels on (tests cover both).
+# convolution kernel more than the activation-sized passes it removes (78.7 ms/step un-fused vs 93.8 fused: the four
+# epilogue warps become the bottleneck), so the un-fused composition is the default; `enabled = True` or
+# SGB_FUSED_CONV=1 switches the fused kernels on (tests cover both).
 enabled = os.environ.get('SGB_FUSED_CONV', '0') == '1'
 
 
