@@ -126,6 +126,12 @@ int sgb_mul_sum_hw(const void* a, const void* b, void* out, int dtype, int n, in
 int sgb_sum_c(const void* a, void* out, int dtype, int n, int c, int h, int w, const int64_t a_strides[4],
               void* stream);
 
+/* In-place nan_to_num over a list of dense fp32 device tensors, 96 tensors per launch: the per-parameter
+ * `param.grad.nan_to_num(nan=0, posinf=1e5, neginf=-1e5)` in front of the optimizer step (train_parts/trainers.py:745-748)
+ * as 1-2 launches per module instead of one per parameter.  ptrs / numels are HOST arrays of length count. */
+int sgb_nan_to_num_multi(void* const* ptrs, const int64_t* numels, int count, float nan, float posinf, float neginf,
+                         void* stream);
+
 /* ---- backward of the convolution's fused epilogue (sgb_conv_desc: out_scale / noise / bias / act / gain / clamp) ----
  * One pass over channels_last (dy, y) replacing bias_act backward + its bias sum (bias_act.py:161-175) and the fma
  * backward passes (fma.py:37-58):   dz = dy * gain * act'(y), masked where |y| >= clamp;

@@ -242,3 +242,44 @@ extern "C" int sgb_sum_c(const void* a, void* out, int dtype, int n, int c, int 
   });
   return 0;
 }
+
+// ---- nan_to_num over a list of tensors (the per-parameter gradient clean-up before the optimizer step) -------------
+namespace sgb {
+constexpr int NTN_MAX = 96;                       // tensors per launch (pointer table travels as a kernel parameter)
+struct NtnParams { float* p[NTN_MAX]; int64_t n[NTN_MAX]; float nan, pinf, ninf; };
+
+__global__ void __launch_bounds__(256) nan_to_num_multi_kernel(NtnParams q) {
+  float* p = q.p[blockIdx.y];
+  const int64_t n = q.n[blockIdx.y];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = p[i];
+    const float r = (v != v) ? q.nan : (v == INFINITY ? q.pinf : (v == -INFINITY ? q.ninf : v));
+    if (!(r == v)) p[i] = r;                      // gradients are almost always finite: read-only pass
+  }
+}
+}  // namespace sgb
+
+extern "C" int sgb_nan_to_num_multi(void* const* ptrs, const int64_t* numels, int count, float nan, float posinf, float neginf,
+                                    void* stream) {
+  SGB_REQUIRE(count >= 0, "negative count");
+  SGB_REQUIRE(count == 0 || (ptrs && numels), "ptrs and numels must not be NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int base = 0; base < count; base += sgb::NTN_MAX) {
+    sgb::NtnParams q; q.nan = nan; q.pinf = posinf; q.ninf = neginf;
+    int m = 0;
+    int64_t largest = 0;
+    for (int i = base; i < count && m < sgb::NTN_MAX; i++) {
+      SGB_REQUIRE(numels[i] >= 0, "negative numel");
+      if (numels[i] == 0) continue;
+      SGB_REQUIRE(ptrs[i] != nullptr, "NULL tensor with numel > 0");
+      q.p[m] = (float*)ptrs[i]; q.n[m] = numels[i]; m++;
+      if (numels[i] > largest) largest = numels[i];
+    }
+    if (m == 0) continue;
+    int64_t bx = sgb::ceil_div(largest, (int64_t)256 * 8); if (bx < 1) bx = 1; if (bx > 64) bx = 64;
+    sgb::nan_to_num_multi_kernel<<<dim3((unsigned)bx, (unsigned)m), 256, 0, st>>>(q);
+    SGB_LAUNCH_CHECK();
+  }
+  return 0;
+}
+

@@ -55,6 +55,7 @@ SIGNATURES = {
     'sgb_mul_sum_hw': (_int, [_vp, _vp, _vp, _int, _int, _int, _int, _int, _c.POINTER(_i64), _c.POINTER(_i64), _vp]),
     'sgb_sum_c': (_int, [_vp, _vp, _int, _int, _int, _int, _int, _c.POINTER(_i64), _vp]),
     'sgb_scale_bias_act': (_int, [_vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _flt, _flt, _flt, _vp]),
+    'sgb_nan_to_num_multi': (_int, [_c.POINTER(_c.c_void_p), _c.POINTER(_i64), _int, _flt, _flt, _flt, _vp]),
     'sgb_mod_bwd': (_int, [_vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp]),
     'sgb_fused_epilogue_bwd': (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _flt, _flt, _flt, _vp]),
 }

@@ -96,6 +96,27 @@ def build_networks(cfg, device):
     return G.to(device), D.to(device)
 
 
+def nan_to_num_(tensors, nan=0.0, posinf=1e5, neginf=-1e5):
+    """In-place `torch.nan_to_num` of every tensor of the list (train_parts/trainers.py:745-748 does it per parameter
+    gradient): dense fp32 CUDA tensors share 1-2 launches (`sgb_nan_to_num_multi`), anything else goes one by one."""
+    import ctypes
+    from . import _lib
+    fast = [t for t in tensors if t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()]
+    for t in tensors:
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            torch.nan_to_num(t, nan=nan, posinf=posinf, neginf=neginf, out=t)
+    by_dev = {}
+    for t in fast:
+        by_dev.setdefault(t.device, []).append(t)
+    for dev, ts in by_dev.items():
+        ptrs = (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+        nums = (ctypes.c_int64 * len(ts))(*[t.numel() for t in ts])
+        with torch.cuda.device(dev):
+            rc = _lib.lib().sgb_nan_to_num_multi(ptrs, nums, len(ts), float(nan), float(posinf), float(neginf), _lib.stream_ptr(dev))
+        _lib.check(rc, 'nan_to_num_multi')
+    return tensors
+
+
 class FlatGradAllReduce:
     """Average the gradients of a parameter list across ranks with a single flat all-reduce."""
 
@@ -234,9 +255,7 @@ class Trainer:
         return val
 
     def _phase_update(self, ph):
-        for p in ph['module'].parameters():
-            if p.grad is not None:
-                torch.nan_to_num(p.grad, nan=0, posinf=1e5, neginf=-1e5, out=p.grad)
+        nan_to_num_([p.grad for p in ph['module'].parameters() if p.grad is not None], nan=0, posinf=1e5, neginf=-1e5)
         ph['opt'].step()
 
     def run_phase(self, ph, real, z):

@@ -191,3 +191,26 @@ def test_cuda_graph_training_iterations():
     assert tr.replayed_launches > 0
     assert any((a - b.detach()).abs().max() > 0 for a, b in zip(p0, tr.G.parameters()))
     assert all(torch.isfinite(p).all() for p in list(tr.G.parameters()) + list(tr.D.parameters()))
+
+
+@pytest.mark.gpu
+def test_multi_tensor_nan_to_num():
+    """sgb_nan_to_num_multi == torch.nan_to_num per tensor (trainers.py:745-748), > 96 tensors, empty and odd sizes."""
+    from sgb200.training import nan_to_num_
+    torch.manual_seed(3)
+    sizes = [0, 1, 3, 7, 512, 1000, 4097, 512 * 9 * 31] + [5 + i for i in range(120)]
+    ts = []
+    for i, n in enumerate(sizes):
+        t = torch.randn(n, device='cuda') * 1e3
+        if n > 0:
+            t[torch.randint(0, n, [max(1, n // 7)], device='cuda')] = float('nan')
+            t[torch.randint(0, n, [max(1, n // 9)], device='cuda')] = float('inf')
+            t[torch.randint(0, n, [max(1, n // 11)], device='cuda')] = float('-inf')
+        ts.append(t)
+    ts.append(torch.randn(6, 5, device='cuda').t())                      # non-contiguous: falls back per tensor
+    ts.append(torch.randn(9, device='cuda', dtype=torch.float16))
+    ts[-1][2] = float('nan')
+    want = [torch.nan_to_num(t, nan=0, posinf=1e5, neginf=-1e5) for t in ts]
+    nan_to_num_(ts, nan=0, posinf=1e5, neginf=-1e5)
+    for a, b in zip(ts, want):
+        assert torch.equal(a, b)
