@@ -134,7 +134,7 @@ static int launch_bias_act(BiasActParams p, cudaStream_t stream) {
   if (vec_ok && p.size_x >= VEC) {
     int64_t nvec = p.size_x / VEC;
     int64_t blocks = ceil_div(nvec, 256 * UNROLL);
-    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
     bias_act_vec_kernel<T, ACT, G, UNROLL><<<(unsigned)blocks, 256, 0, stream>>>(p);
     SGB_LAUNCH_CHECK();
     done = nvec * VEC;
@@ -142,7 +142,7 @@ static int launch_bias_act(BiasActParams p, cudaStream_t stream) {
   if (done < p.size_x) {
     int64_t rest = p.size_x - done;
     int64_t blocks = ceil_div(rest, 256);
-    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
     bias_act_scalar_kernel<T, ACT, G><<<(unsigned)blocks, 256, 0, stream>>>(p, done);
     SGB_LAUNCH_CHECK();
   }
@@ -252,12 +252,12 @@ extern "C" int sgb_sum_to_channel(const void* x, void* out, int dtype, int64_t o
     if (inner == 1) {
       int64_t gx = ceil_div(size_c, 32);
       int64_t gy = ceil_div(outer, 8 * 16); if (gy < 1) gy = 1;
-      int64_t cap = ceil_div((int64_t)kNumSMs * 8, gx); if (gy > cap) gy = cap; if (gy > 65535) gy = 65535;
+      int64_t cap = ceil_div((int64_t)num_sms() * 8, gx); if (gy > cap) gy = cap; if (gy > 65535) gy = 65535;
       SGB_REQUIRE(gx <= 0x7fffffff, "too many channels");
       sum_to_channel_last_kernel<T><<<dim3((unsigned)gx, (unsigned)gy), dim3(32, 8), 0, s>>>((const T*)x, (Acc<T>::type*)out, outer, size_c);
     } else {
       SGB_REQUIRE(size_c <= 0x7fffffff, "too many channels");
-      int64_t gy = ceil_div((int64_t)kNumSMs * 4, size_c); if (gy > outer) gy = outer; if (gy < 1) gy = 1;
+      int64_t gy = ceil_div((int64_t)num_sms() * 4, size_c); if (gy > outer) gy = outer; if (gy < 1) gy = 1;
       if (gy > 65535) gy = 65535;
       sum_to_channel_inner_kernel<T><<<dim3((unsigned)size_c, (unsigned)gy), 256, 0, s>>>((const T*)x, (Acc<T>::type*)out, outer, size_c, inner);
     }

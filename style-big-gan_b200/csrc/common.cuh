@@ -10,7 +10,24 @@
 
 namespace sgb {
 
-constexpr int kNumSMs = 148;   // B200
+// SM count of the current device (148 on a B200), queried once per device ordinal
+int num_sms();
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: set it once per (kernel instantiation, device),
+// from whichever thread launches first (forward runs on the caller's thread, backward on autograd's worker threads).
+// Use inside the templated launcher of `kern` so that the static table is per instantiation.
+#define SGB_SET_MAX_SMEM(kern, bytes)                                                                    \
+  do {                                                                                                   \
+    static std::atomic<int> done_[64];                                                                   \
+    int dev_ = 0;                                                                                        \
+    cudaGetDevice(&dev_);                                                                                \
+    const int want_ = (int)(bytes);                                                                      \
+    if (dev_ < 0 || dev_ >= 64 || done_[dev_].load(std::memory_order_acquire) < want_) {                 \
+      cudaError_t e_ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, want_);   \
+      SGB_REQUIRE(e_ == cudaSuccess, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e_));    \
+      if (dev_ >= 0 && dev_ < 64) done_[dev_].store(want_, std::memory_order_release);                   \
+    }                                                                                                    \
+  } while (0)
 
 // ---- error reporting (thread-local text, non-zero return codes; never abort) ----
 void set_error(const std::string& msg);

@@ -37,8 +37,9 @@ static int validate(const sgb_conv_desc* d) {
 
 using namespace sgb;
 
-// 2 = halo-tile tensor-core kernel, 1 = per-tap tensor-core kernel (16-bit types only: kind::tf32 does not take the
-// MN-major operands the weight gradient needs; fp32 runs the 3 x bf16 split inside the halo kernel), 0 = SIMT
+// 2 = halo-tile tensor-core kernels (16-bit: conv_wgrad_halo_kernel; fp32: conv_wgrad_tf32_kernel on kind::tf32 with the
+// SWIZZLE_128B_BASE32B operand layout, or the 3 x bf16 split with SGB_WGRAD_FP32=split), 1 = per-tap tensor-core kernel
+// (16-bit types, geometries the halo kernels do not take), 0 = SIMT
 static int wgrad_route(const sgb_conv_desc* d) {
   if (!conv_wgrad_umma_eligible(d)) return 0;
   if (conv_wgrad_halo_eligible(d)) return 2;

@@ -66,7 +66,7 @@ static int pick_gt(const sgb_conv_desc* d, int mode, int bn) {
   // do not pad narrow images, keep every SM busy
   const bool keep_cols = (mode == 2 && m2gt);      // experiment: accept the padded last column tile
   while (gt > 1 && ((!keep_cols && cols % (8 * gt) != 0) ||
-                    ceil_div((int64_t)d->n * rows, 16) * ceil_div(cols, 8 * gt) * ntiles < kNumSMs)) gt >>= 1;
+                    ceil_div((int64_t)d->n * rows, 16) * ceil_div(cols, 8 * gt) * ntiles < num_sms())) gt >>= 1;
   return gt;
 }
 

@@ -559,13 +559,8 @@ int launch_halo(const sgb_conv_desc* d, const void* x, const void* w, void* y, c
   p.stg_off = sa * p.a_stage_bytes + sb * b_stage;
   const size_t smem = (size_t)p.stg_off + stg_bytes + 1024;
   auto kern = conv_halo_kernel<T, KIND, BN, MODE, GT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-    SGB_REQUIRE(e == cudaSuccess, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
-    attr_set = true;
-  }
-  const int64_t grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
+  SGB_SET_MAX_SMEM(kern, 226 * 1024);
+  const int64_t grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   kern<<<(unsigned)grid, HALO_THREADS, smem, s>>>(p);
   SGB_LAUNCH_CHECK();
   return 0;

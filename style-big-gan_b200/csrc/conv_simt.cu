@@ -276,7 +276,7 @@ int conv_wgrad_simt(const sgb_conv_desc* d, const void* x, const void* dy, void*
   if (P == 0) return 0;
   const int taps = d->kh * d->kw;
   const int64_t gx = ceil_div(p.co_g, BM), gy = ceil_div(p.ci_g, BN) * taps;
-  int64_t splits = ceil_div((int64_t)kNumSMs * 4, gx * gy * d->groups);
+  int64_t splits = ceil_div((int64_t)num_sms() * 4, gx * gy * d->groups);
   const int64_t max_splits = ceil_div(P, 4 * BK);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;

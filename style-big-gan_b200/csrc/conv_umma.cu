@@ -462,7 +462,7 @@ int pack_weights_umma(const sgb_conv_desc* d, const void* w, int bn, cudaStream_
   const int tc = 16 / elem_size(d->dtype);
   const int ntiles = (d->co + bn - 1) / bn, cblocks = (d->ci + 8 * tc - 1) / (8 * tc);
   const int64_t total = (int64_t)ntiles * d->kh * d->kw * cblocks * 8 * bn * tc;
-  int64_t blocks = ceil_div(total, 256); if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  int64_t blocks = ceil_div(total, 256); if (blocks > num_sms() * 8) blocks = num_sms() * 8;
   if (d->dtype == SGB_F16)       pack_weights_kernel<__half, 0><<<(unsigned)blocks, 256, 0, s>>>((const __half*)w, d->workspace, *d, bn, ntiles, cblocks, tc);
   else if (d->dtype == SGB_BF16) pack_weights_kernel<__nv_bfloat16, 1><<<(unsigned)blocks, 256, 0, s>>>((const __nv_bfloat16*)w, d->workspace, *d, bn, ntiles, cblocks, tc);
   else                           pack_weights_kernel<float, 2><<<(unsigned)blocks, 256, 0, s>>>((const float*)w, d->workspace, *d, bn, ntiles, cblocks, tc);
@@ -499,12 +499,7 @@ static int launch_umma(const sgb_conv_desc* d, const void* x, const void* w, voi
   // 2) implicit GEMM
   const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + BN * KB_BYTES) + 1024;
   auto kern = conv_umma_kernel<T, KIND, BN, STAGES>;
-  static bool attr_set = false;          // per template instantiation
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    SGB_REQUIRE(e == cudaSuccess, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
-    attr_set = true;
-  }
+  SGB_SET_MAX_SMEM(kern, (int)smem);
   const int64_t gx = ceil_div(p.M, UM);
   SGB_REQUIRE(gx <= 0x7fffffff && p.ntiles <= 65535, "problem too large for the UMMA conv grid");
   kern<<<dim3((unsigned)gx, (unsigned)p.ntiles), 192, smem, s>>>(p);
@@ -554,7 +549,7 @@ static int launch_wgrad_umma(const sgb_conv_desc* d, const void* x, const void* 
   p.ctiles = (d->ci + BNC - 1) / BNC; p.otiles = (d->co + UM - 1) / UM;
   SGB_REQUIRE(aligned16(x) && aligned16(dy), "x and dy must be 16-byte aligned");
   const int64_t tiles = (int64_t)p.otiles * p.ctiles * p.taps;
-  int64_t splits = ceil_div((int64_t)kNumSMs * 2, tiles);
+  int64_t splits = ceil_div((int64_t)num_sms() * 2, tiles);
   const int64_t max_splits = ceil_div(p.P, (int64_t)PPB * 8);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
@@ -564,12 +559,7 @@ static int launch_wgrad_umma(const sgb_conv_desc* d, const void* x, const void* 
   SGB_REQUIRE((int64_t)p.ctiles * p.taps <= 65535 && splits <= 65535, "problem too large for the UMMA wgrad grid");
   const size_t smem = (size_t)STAGES * (UM * PPB * sizeof(T) + BNC * PPB * sizeof(T)) + 1024;
   auto kern = conv_wgrad_umma_kernel<T, KIND, BNC, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    SGB_REQUIRE(e == cudaSuccess, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
-    attr_set = true;
-  }
+  SGB_SET_MAX_SMEM(kern, (int)smem);
   kern<<<dim3((unsigned)p.otiles, (unsigned)(p.ctiles * p.taps), (unsigned)splits), 160, smem, s>>>(p);
   SGB_LAUNCH_CHECK();
   return 0;

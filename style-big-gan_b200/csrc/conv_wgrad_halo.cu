@@ -595,7 +595,7 @@ static int launch_wgrad_halo(const sgb_conv_desc* d, const void* x, const void* 
   p.row_tiles = (d->out_h + TH - 1) / TH; p.col_tiles = (d->out_w + 7) / 8;
   p.total_tiles = (int64_t)d->n * p.row_tiles * p.col_tiles;
   const int64_t base = (int64_t)otiles * p.ctiles * d->kh;
-  int64_t splits = kNumSMs / base; if (splits < 1) splits = 1;
+  int64_t splits = num_sms() / base; if (splits < 1) splits = 1;
   if (splits > p.total_tiles) splits = p.total_tiles;
   p.chunk_tiles = ceil_div(p.total_tiles, splits);
   splits = ceil_div(p.total_tiles, p.chunk_tiles);
@@ -603,12 +603,7 @@ static int launch_wgrad_halo(const sgb_conv_desc* d, const void* x, const void* 
   SGB_REQUIRE(aligned16(x) && aligned16(dy), "x and dy must be 16-byte aligned");
   const size_t smem = (size_t)stages * p.stage_bytes + 1024;
   auto kern = conv_wgrad_halo_kernel<T, KIND, BNC>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-    SGB_REQUIRE(e == cudaSuccess, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
-    attr_set = true;
-  }
+  SGB_SET_MAX_SMEM(kern, 226 * 1024);
   kern<<<dim3((unsigned)otiles, (unsigned)(p.ctiles * d->kh), (unsigned)splits), WG_THREADS, smem, st>>>(p);
   SGB_LAUNCH_CHECK();
   return 0;
@@ -648,7 +643,7 @@ static int launch_wgrad_split(const sgb_conv_desc* d, const void* x, const void*
   p.row_tiles = (d->out_h + TH - 1) / TH; p.col_tiles = (d->out_w + 7) / 8;
   p.total_tiles = (int64_t)d->n * p.row_tiles * p.col_tiles;
   const int64_t base = (int64_t)otiles * p.ctiles * d->kh;
-  int64_t splits = kNumSMs / base; if (splits < 1) splits = 1;
+  int64_t splits = num_sms() / base; if (splits < 1) splits = 1;
   if (splits > p.total_tiles) splits = p.total_tiles;
   p.chunk_tiles = ceil_div(p.total_tiles, splits);
   splits = ceil_div(p.total_tiles, p.chunk_tiles);
@@ -656,12 +651,7 @@ static int launch_wgrad_split(const sgb_conv_desc* d, const void* x, const void*
   SGB_REQUIRE(aligned16(x) && aligned16(dy), "x and dy must be 16-byte aligned");
   const size_t smem = (size_t)(nstg + stages) * p.stage_bytes + 1024;
   auto kern = conv_wgrad_split_kernel<BNC>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-    SGB_REQUIRE(e == cudaSuccess, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
-    attr_set = true;
-  }
+  SGB_SET_MAX_SMEM(kern, 226 * 1024);
   kern<<<dim3((unsigned)otiles, (unsigned)(p.ctiles * d->kh), (unsigned)splits), WS_THREADS, smem, st>>>(p);
   SGB_LAUNCH_CHECK();
   return 0;

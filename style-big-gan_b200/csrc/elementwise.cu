@@ -183,10 +183,10 @@ extern "C" int sgb_scale_nc(const void* x, const void* s, const void* t, void* y
       int64_t gx = ceil_div(hw / VEC, 256); if (gx > 64) gx = 64;
       scale_nc_plane_kernel<T><<<dim3((unsigned)gx, (unsigned)gy, (unsigned)gz), 256, 0, st>>>(p);
     } else if (al && dense_nhwc(p.as, c, h, w) && dense_nhwc(p.ys, c, h, w) && c % VEC == 0) {
-      int64_t blocks = ceil_div(total / VEC, 256); if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+      int64_t blocks = ceil_div(total / VEC, 256); if (blocks > num_sms() * 16) blocks = num_sms() * 16;
       scale_nc_cl_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(p);
     } else {
-      int64_t blocks = ceil_div(total, 256); if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+      int64_t blocks = ceil_div(total, 256); if (blocks > num_sms() * 16) blocks = num_sms() * 16;
       scale_nc_generic_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(p, (y_strides[1] == 1 && c > 1) ? 1 : 0);
     }
     SGB_LAUNCH_CHECK();
@@ -232,10 +232,10 @@ extern "C" int sgb_sum_c(const void* a, void* out, int dtype, int n, int c, int 
   cudaStream_t st = (cudaStream_t)stream;
   SGB_DISPATCH_DTYPE(dtype, {
     if (a_strides[1] == 1 && c > 1) {
-      int64_t blocks = ceil_div(total, 8); if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+      int64_t blocks = ceil_div(total, 8); if (blocks > num_sms() * 16) blocks = num_sms() * 16;
       sum_c_cl_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(p);
     } else {
-      int64_t blocks = ceil_div(total, 256); if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+      int64_t blocks = ceil_div(total, 256); if (blocks > num_sms() * 16) blocks = num_sms() * 16;
       sum_c_plane_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(p);
     }
     SGB_LAUNCH_CHECK();

@@ -137,7 +137,7 @@ extern "C" int sgb_fused_epilogue_bwd(const void* dy, const void* y, void* dconv
   p.alpha = (act == SGB_ACT_LINEAR) ? 1.f : alpha; p.gain = gain; p.clamp = clamp;
   // ~4 blocks per SM in total, whole blocks inside one image
   const int cvt = c / vec, lanes = 256 / cvt;
-  int64_t want = ((int64_t)kNumSMs * 4 + n - 1) / n;               // blocks per image
+  int64_t want = ((int64_t)num_sms() * 4 + n - 1) / n;               // blocks per image
   int64_t maxb = ((int64_t)hw + lanes - 1) / lanes;                // at least one pixel per lane
   if (want > maxb) want = maxb;
   if (want < 1) want = 1;
@@ -211,7 +211,7 @@ extern "C" int sgb_scale_bias_act(const void* x, const void* bias, const void* o
   p.x = x; p.y = y; p.bias = bias; p.out_scale = (const float*)out_scale; p.noise = (const float*)noise;
   p.n = n; p.c = c; p.hw = hw; p.alpha = (act == SGB_ACT_LINEAR) ? 1.f : alpha; p.gain = gain; p.clamp = clamp;
   const int64_t nv = (int64_t)n * hw * (c / vec);
-  int64_t blocks = sgb::ceil_div(nv, 512); if (blocks > sgb::kNumSMs * 8) blocks = sgb::kNumSMs * 8;
+  int64_t blocks = sgb::ceil_div(nv, 512); if (blocks > sgb::num_sms() * 8) blocks = sgb::num_sms() * 8;
   cudaStream_t s = (cudaStream_t)stream;
   switch (dtype) {
     case SGB_F32:  sgb::scale_bias_act_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(p); break;
@@ -302,7 +302,7 @@ extern "C" int sgb_mod_bwd(const void* g, const void* x, const void* s, void* gx
   sgb::ModBwdParams p;
   p.g = g; p.x = x; p.s = (const float*)s; p.gx = gx; p.gs = (float*)gs; p.n = n; p.c = c; p.hw = hw;
   const int cvt = c / vec, lanes = 256 / cvt;
-  int64_t want = ((int64_t)sgb::kNumSMs * 4 + n - 1) / n;
+  int64_t want = ((int64_t)sgb::num_sms() * 4 + n - 1) / n;
   int64_t maxb = ((int64_t)hw + lanes - 1) / lanes;
   if (want > maxb) want = maxb;
   if (want < 1) want = 1;

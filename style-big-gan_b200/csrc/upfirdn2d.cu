@@ -283,7 +283,7 @@ static int launch_upfirdn(const UpfirdnParams& p, cudaStream_t s) {
     }
   }
   int64_t blocks = ceil_div(total, 256);
-  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  if (blocks > num_sms() * 16) blocks = num_sms() * 16;
   upfirdn2d_generic_kernel<T><<<(unsigned)blocks, 256, 0, s>>>(p);
   SGB_LAUNCH_CHECK();
   return 0;

@@ -21,6 +21,12 @@ enabled = True                      # kept for API compatibility; the custom op 
 use_tensor_cores = True             # False routes every convolution to the SIMT kernels (debugging / A-B tests)
 use_halo_kernel = True              # False keeps tensor cores but skips the halo-tile kernels (A-B tests)
 halo_gt = 0                         # tiles per super-tile of the halo-tile kernel: 0 = automatic, 1 / 2 / 4 forced (tests, tuning)
+channels_last_for_tensor_cores = True   # NCHW operands of a convolution that is otherwise eligible for the tensor-core kernels are
+                                    # re-laid out to channels_last (one pass) and the result is returned channels_last -- same
+                                    # logical shape, different strides; what cuDNN does internally for its NHWC tensor-core
+                                    # kernels.  This is how the reference's unchanged callers (fp32 blocks are NCHW,
+                                    # generators.py:392, discriminators.py:247) reach the tcgen05 kernels.  False = such
+                                    # operands run the SIMT kernels and keep their layout.
 weight_gradients_disabled = False   # forcefully disable computation of gradients with respect to the weights
 
 
@@ -214,6 +220,8 @@ def _conv2d_op(transpose, weight_shape, stride, padding, output_padding, dilatio
                 w = _pad_dim(w, 0 if transpose else 1, mult)
                 sc = _pad_dim(sc, 1, mult) if sc is not None else None
                 ci_, fmt = x_.shape[1], torch.channels_last
+            elif mult and channels_last_for_tensor_cores and input.numel() > 0 and not _lib.is_channels_last(input):
+                x_, fmt = input.contiguous(memory_format=torch.channels_last), torch.channels_last
             y = torch.empty([input.shape[0], co, oh, ow], dtype=input.dtype, device=input.device, memory_format=fmt)
             b = bias.contiguous() if bias is not None else None
             if y.numel() > 0:
@@ -259,6 +267,11 @@ def _conv2d_op(transpose, weight_shape, stride, padding, output_padding, dilatio
         is the adjoint of the conv2d that maps the op's output space to its input space."""
         @staticmethod
         def forward(ctx, grad_output, input, in_scale):
+            go_, in_ = grad_output, input
+            if (_tc_multiple(input, groups) and channels_last_for_tensor_cores and input.numel() > 0 and grad_output.numel() > 0
+                    and ci % _tc_multiple(input, groups) == 0 and co % _tc_multiple(input, groups) == 0):
+                grad_output = grad_output.contiguous(memory_format=torch.channels_last)
+                input = input.contiguous(memory_format=torch.channels_last)
             if not transpose:
                 x_, dy_, sc = input, grad_output, _scale_arg(in_scale, input)
                 d = _make_desc(x_, dy_, False, ci, co, kh, kw, s, padding, groups, flip, sc)
@@ -304,7 +317,7 @@ def _conv2d_op(transpose, weight_shape, stride, padding, output_padding, dilatio
             # the non-transposed layout [C(dy_), C(x_), kh, kw] is the op's weight layout in both cases:
             # conv2d: [co, ci]; conv_transpose2d (x_ = grad_output, dy_ = input): [ci, co]
             dw = dwf.reshape(weight_shape) if not padded else dwf.contiguous().reshape(weight_shape)
-            ctx.save_for_backward(grad_output, input, in_scale)
+            ctx.save_for_backward(go_, in_, in_scale)
             return dw.to(input.dtype)
 
         @staticmethod

@@ -150,9 +150,10 @@ class Trainer:
         self.cfg, self.device, self.rank, self.world_size = cfg, torch.device(device), rank, world_size
         torch.manual_seed(cfg.seed * world_size + rank)       # trainers.py:507-508
         self.G, self.D = build_networks(cfg, self.device)
-        if world_size > 1:      # same initial weights on every rank (DDP broadcasts them at construction)
-            for p in list(self.G.parameters()) + list(self.D.parameters()):
-                dist.broadcast(p.data, src=0)
+        if world_size > 1:      # same initial state on every rank: DistributedDataParallel broadcasts parameters AND buffers
+            for t in (list(self.G.parameters()) + list(self.G.buffers()) +      # (noise_const, w_avg, ...) from rank 0 at construction
+                      list(self.D.parameters()) + list(self.D.buffers())):
+                dist.broadcast(t.data, src=0)
         self.G_ema = copy.deepcopy(self.G).eval().requires_grad_(False) if cfg.use_ema else None
         self.G.train().requires_grad_(False)
         self.D.train().requires_grad_(False)
@@ -176,6 +177,8 @@ class Trainer:
         # CUDA-graph state (cfg.cuda_graphs): static inputs, one graph pair per phase, shared memory pool
         self._graphs = None
         self.replayed_launches = 0      # libsgb200 kernel launches executed through graph replays
+        self.static_z = None            # tests: {phase name: z tensor} captured as a static graph input instead of torch.randn
+        self.static_pl_noise = None     # tests: the path-length noise image [N/2,3,R,R] instead of torch.randn_like
 
     # ---- forward helpers (losses_base.py:131-156)
     def run_G(self, z, return_ws=False):
@@ -246,7 +249,7 @@ class Trainer:
         if name == 'Gmain':
             val = self.phase_Gmain(z, gain)
         elif name == 'Greg':
-            val = self.phase_Greg(z, gain)
+            val = self.phase_Greg(z, gain, pl_noise=self.static_pl_noise)
         elif name == 'Dmain':
             val = self.phase_Dmain(z, real, gain)
         else:
@@ -266,6 +269,8 @@ class Trainer:
 
     # ---- CUDA graphs: every phase is static-shaped, so its ~1000 launches are captured once and replayed ----
     def _real_from_u8(self, real_u8):
+        if real_u8.is_floating_point():                         # tests: images already in [-1, 1]
+            return real_u8
         return real_u8.to(torch.float32) / 127.5 - 1            # trainers.py:716
 
     def _ema_update(self):
@@ -279,6 +284,32 @@ class Trainer:
             for b_ema, b in zip(self.G_ema.buffers(), self.G.buffers()):
                 b_ema.copy_(b)
 
+    def _snapshot_state(self):
+        mods = [m for m in (self.G, self.D, self.G_ema) if m is not None]
+        opts = {id(ph['opt']): ph['opt'] for ph in self.phases}.values()
+        return dict(mods=[{k: v.detach().clone() for k, v in m.state_dict().items()} for m in mods],
+                    opts=[copy.deepcopy(o.state_dict()) for o in opts], pl_mean=self.pl_mean.clone(),
+                    rng=torch.cuda.get_rng_state(self.device))
+
+    def _restore_state(self, snap):
+        mods = [m for m in (self.G, self.D, self.G_ema) if m is not None]
+        opts = {id(ph['opt']): ph['opt'] for ph in self.phases}.values()
+        with torch.no_grad():
+            for m, sd in zip(mods, snap['mods']):
+                for k, v in m.state_dict().items():
+                    v.copy_(sd[k])
+            for o, sd in zip(opts, snap['opts']):
+                if sd['state']:
+                    o.load_state_dict(sd)
+                    continue
+                # fresh optimizer: keep the (lazily created) state tensors, reset exp_avg / exp_avg_sq / step to zero
+                for st_ in o.state.values():
+                    for v in st_.values():
+                        if torch.is_tensor(v):
+                            v.zero_()
+            self.pl_mean.copy_(snap['pl_mean'])
+        torch.cuda.set_rng_state(snap['rng'], self.device)
+
     def _build_graphs(self, real_u8):
         from . import _lib
         cfg = self.cfg
@@ -286,7 +317,10 @@ class Trainer:
         multi = self.world_size > 1
         st = dict(real_u8=torch.empty_like(real_u8), graphs={}, pool=None)
         st['real_u8'].copy_(real_u8)
-        # eager warm-up on a side stream: lazy initialisation (optimizer state, kernel attributes, library handles)
+        # eager warm-up on a side stream: lazy initialisation (optimizer state, kernel attributes, library handles).
+        # The warm-up runs real optimizer steps, so the training state is snapshotted before and restored after it:
+        # iteration 0 of a graph-replayed run starts from the same weights / Adam moments / pl_mean / w_avg as an eager run.
+        snap = self._snapshot_state()
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -299,13 +333,16 @@ class Trainer:
                     self._ema_update()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        self._restore_state(snap)
         pool = torch.cuda.graph_pool_handle()
         for ph in self.phases:
             g1 = torch.cuda.CUDAGraph()
             n0 = _lib.launch_count()
             with torch.cuda.graph(g1, pool=pool):
                 real = self._real_from_u8(st['real_u8'])
-                z = torch.randn([cfg.batch_gpu, cfg.z_dim], device=dev)
+                z = (self.static_z or {}).get(ph['name'])
+                if z is None:
+                    z = torch.randn([cfg.batch_gpu, cfg.z_dim], device=dev)
                 val = self._phase_grads(ph, real, z)
                 if not multi:
                     self._phase_update(ph)

@@ -341,3 +341,64 @@ def test_small_co_1x1_kernel(dtype, case):
         assert_close(y, yo.detach(), TOL, f'{case} {dtype} y scale={scale is not None}')
         for g, go, name in zip(grads, gos, ('dx', 'dw', 'ds')):
             assert_close(g, go, TOL, f'{case} {dtype} {name} scale={scale is not None}')
+
+
+# ---- second-order gradients THROUGH the tensor-core kernels --------------------------------------------------------
+# conv2d_gradfix.py:119-165 of the reference: the backward of a convolution is the other convolution + Conv2dGradWeight, whose own
+# backward is two more convolutions.  R1 differentiates |d logits / d image|^2 wrt the weights (dgrad -> its weight gradient);
+# a gradient penalty without no_weight_gradients() differentiates dw itself (Conv2dGradWeight.backward).  Oracle: the same
+# expressions with torch.nn.functional.conv2d in fp64 on the CPU (what the reference's ops resolve to).
+def _second_order_terms(conv, x, w, dy, v_x, v_w):
+    y = conv(x, w)
+    dx, dw = torch.autograd.grad(y, [x, w], dy, create_graph=True)
+    # (i) R1 style: L1 = <dx, dx> ; (ii) full: L2 = <dx, v_x> + <dw, v_w>, differentiated wrt x, w and dy
+    L1 = dx.square().sum()
+    g1_w, g1_dy = torch.autograd.grad(L1, [w, dy], retain_graph=True)
+    L2 = (dx * v_x).sum() + (dw * v_w).sum()
+    g2_x, g2_w, g2_dy = torch.autograd.grad(L2, [x, w, dy])
+    return dict(y=y, dx=dx, dw=dw, g1_w=g1_w, g1_dy=g1_dy, g2_x=g2_x, g2_w=g2_w, g2_dy=g2_dy)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16])
+@pytest.mark.parametrize('case', [
+    # (N, Ci, Co, H, k, stride, pad, transposed)
+    (4, 64, 64, 32, 3, 1, 1, False),       # stride-1 3x3 (conv1 of every block)
+    (4, 128, 64, 16, 3, 2, 0, True),       # transposed stride 2 (G up path)
+    (4, 64, 128, 33, 3, 2, 0, False),      # stride 2 after the FIR (D down path)
+    (2, 256, 256, 8, 3, 1, 1, False),      # two K blocks of 128, BN = 256
+    (4, 64, 64, 16, 1, 1, 0, False),       # 1x1 (skip / fromRGB geometry)
+])
+def test_tensor_core_double_backward(dtype, case):
+    from sgb200.ops import conv2d_gradfix as cg
+    from sgb200 import _lib
+    n, ci, co, h, k, stride, pad, tr = case
+    torch.manual_seed(11)
+    torch.backends.cudnn.allow_tf32 = True
+    wshape = (ci, co, k, k) if tr else (co, ci, k, k)
+    x0 = torch.randn(n, ci, h, h)
+    w0 = torch.randn(wshape) / math.sqrt(ci * k * k)
+    fo = torch.nn.functional.conv_transpose2d if tr else torch.nn.functional.conv2d
+    yo_shape = fo(x0, w0, stride=stride, padding=pad).shape
+    dy0, vx0, vw0 = torch.randn(yo_shape), torch.randn(n, ci, h, h), torch.randn(wshape)
+
+    def leaf(t, dev, dt, cl=False):
+        t = t.to(dev, dt)
+        if cl and t.ndim == 4:
+            t = t.contiguous(memory_format=torch.channels_last)
+        return t.requires_grad_(True)
+
+    ref = _second_order_terms(lambda a, b: fo(a, b, stride=stride, padding=pad),
+                              leaf(x0, 'cpu', torch.float64), leaf(w0, 'cpu', torch.float64), leaf(dy0, 'cpu', torch.float64),
+                              vx0.double(), vw0.double())
+    op = cg.conv_transpose2d if tr else cg.conv2d
+    _lib.profile_start()
+    got = _second_order_terms(lambda a, b: op(a, b, stride=stride, padding=pad),
+                              leaf(x0, DEV, dtype, True), leaf(w0, DEV, dtype), leaf(dy0, DEV, dtype, True),
+                              vx0.to(DEV, dtype).contiguous(memory_format=torch.channels_last), vw0.to(DEV, dtype))
+    torch.cuda.synchronize()
+    summ = _lib.profile_stop().summary()
+    assert 'conv_fwd_simt' not in summ and 'conv_wgrad_simt' not in summ, f'SIMT fallback in the tensor-core test: {sorted(summ)}'
+    assert summ['conv_fwd_tc']['launches'] >= 6 and summ['conv_wgrad_tc']['launches'] >= 3, summ
+    tol = 1e-2 if dtype == torch.float32 else 2e-2       # fp16 second-order terms: inputs AND first-order results are rounded to fp16
+    for key in ref:
+        assert_close(got[key].float(), ref[key].float(), tol, f'{case} {dtype} {key}')

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import GOLDEN, assert_close
+from helpers import GOLDEN, assert_close, check_phase_grads as _check
 from oracle import ref_networks as RN
 
 DEV = 'cuda'
@@ -69,34 +69,27 @@ def test_forward_matches_reference_golden(gold, channels_last):
     assert_close(logits, torch.from_numpy(z['logits']), 1e-4, 'logits')
 
 
-def _check(z, phase, tag, module, tol):
-    """Per-tensor max-norm relative error.  Tensors whose reference gradient is more than 100x smaller than
-    the phase's largest one (e.g. D biases under R1: they only receive second-order signal through the
-    minibatch-stddev layer, ~1e-8 against 1e-2 for the weights) are measured against that floor instead of
-    their own tiny norm, where fp32 summation order alone exceeds any relative tolerance."""
-    keys = [k for k in z.files if k.startswith(f'{phase}.grad.{tag}')]
-    assert keys
-    named = dict(module.named_parameters())
-    floor = 1e-2 * max(float(np.abs(z[k]).max()) for k in keys)
-    for k in keys:
-        name = k[len(f'{phase}.grad.{tag}'):]
-        assert named[name].grad is not None, f'{phase}: no grad for {name}'
-        ref = torch.from_numpy(z[k])
-        got = named[name].grad.detach().cpu()
-        assert got.shape == ref.shape
-        err = (got.double() - ref.double()).abs().max().item() / max(ref.abs().max().item(), floor)
-        assert err <= tol, f'{phase} {name}: rel err {err:.3e} > {tol:.1e}'
+# arithmetic modes of the training-phase parity tests (same table as tests/test_ref_callers_gpu.py):
+#   strict = fp32 FFMA kernels (reference default allow_tf32=False);  tf32 = tcgen05 kind::tf32 forward / dgrad / wgrad, the
+#   arithmetic bench.py measures;  fp16 = num_fp16_res=2 + conv_clamp=256 (+ TF32 in the fp32 blocks), against the fp32 golden
+MODES = {
+    'strict': dict(tf32=False, over={}, tol1=2e-4, tol2=5e-4),
+    'tf32': dict(tf32=True, over={}, tol1=1e-2, tol2=1e-2),
+    'fp16': dict(tf32=True, over=dict(num_fp16_res=2, conv_clamp=256.0), tol1=1e-2, tol2=2e-2),
+}
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('channels_last', [False, True])
-def test_training_phases_match_reference_golden(gold, channels_last):
+@pytest.mark.parametrize('mode,channels_last', [('strict', False), ('strict', True), ('tf32', True), ('tf32', False), ('fp16', True)])
+def test_training_phases_match_reference_golden(gold, mode, channels_last):
     """Gradients of every parameter for Gmain, Dmain, Dreg (R1) and Greg (path length) -- the last two are
     double backward through conv / upfirdn2d / bias_act / modulation -- against the reference's own
     SG2Loss / R1reg / PPLreg run on CPU (oracle/make_golden.py)."""
     from sgb200 import training
     z, meta = gold
-    cfg, _, _ = _build(meta, 'cpu', channels_last=channels_last)
+    m = MODES[mode]
+    torch.backends.cudnn.allow_tf32 = m['tf32']          # restored by conftest's autouse fixture
+    cfg, _, _ = _build(meta, 'cpu', channels_last=channels_last, **m['over'])
     tr = training.Trainer(cfg, DEV)
     _load(z, tr.G, tr.D)
     zz = torch.from_numpy(z['z']).to(DEV)
@@ -112,12 +105,55 @@ def test_training_phases_match_reference_golden(gold, channels_last):
         mod.requires_grad_(False)
         return mod
 
-    _check(z, 'Gmain', 'G.', run('Gmain', lambda: tr.phase_Gmain(zz, gains['Gmain'])), 2e-4)
-    _check(z, 'Dmain', 'D.', run('Dmain', lambda: tr.phase_Dmain(zz, real, gains['Dmain'])), 2e-4)
-    _check(z, 'Dreg', 'D.', run('Dreg', lambda: tr.phase_Dreg(real, gains['Dreg'])), 5e-4)
+    _check(z, 'Gmain', 'G.', run('Gmain', lambda: tr.phase_Gmain(zz, gains['Gmain'])), m['tol1'])
+    _check(z, 'Dmain', 'D.', run('Dmain', lambda: tr.phase_Dmain(zz, real, gains['Dmain'])), m['tol1'])
+    _check(z, 'Dreg', 'D.', run('Dreg', lambda: tr.phase_Dreg(real, gains['Dreg'])), m['tol2'])
     pl_noise = torch.from_numpy(z['pl_noise']).to(DEV)
     tr.pl_mean.zero_()
-    _check(z, 'Greg', 'G.', run('Greg', lambda: tr.phase_Greg(zz, gains['Greg'], pl_noise=pl_noise)), 5e-4)
+    _check(z, 'Greg', 'G.', run('Greg', lambda: tr.phase_Greg(zz, gains['Greg'], pl_noise=pl_noise)), m['tol2'])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('mode', ['strict', 'tf32', 'fp16'])
+def test_cuda_graph_phases_match_golden_and_eager(gold, mode):
+    """The benched launch mode: every phase captured in a CUDA graph (TrainConfig.cuda_graphs) with z, the real images and the
+    path-length noise as static inputs.  The gradients a replay leaves behind must match (a) the reference golden and (b)
+    the same phase launched eagerly, and the warm-up that precedes the capture must not have advanced the training state."""
+    from sgb200 import training
+    z, meta = gold
+    m = MODES[mode]
+    torch.backends.cudnn.allow_tf32 = m['tf32']
+    cfg, _, _ = _build(meta, 'cpu', channels_last=True, cuda_graphs=True, lr=0.0, **m['over'])     # lr 0: all four phases see
+    tr = training.Trainer(cfg, DEV)                                                                # the golden weights
+    _load(z, tr.G, tr.D)
+    w0 = [p.detach().clone() for p in list(tr.G.parameters()) + list(tr.D.parameters())]
+    zz = torch.from_numpy(z['z']).to(DEV)
+    real = torch.from_numpy(z['real']).to(DEV)
+    tr.static_z = {n: zz for n in ('Gmain', 'Greg', 'Dmain', 'Dreg')}
+    tr.static_pl_noise = torch.from_numpy(z['pl_noise']).to(DEV)
+    assert meta['gains'] == dict(Gmain=1, Dmain=1, Dreg=cfg.d_reg_interval, Greg=cfg.g_reg_interval)
+    out = tr.iteration(real, force_all_phases=True)
+    torch.cuda.synchronize()
+    assert sorted(out) == ['Dmain', 'Dreg', 'Gmain', 'Greg'] and tr.replayed_launches > 0
+    for a, b in zip(w0, list(tr.G.parameters()) + list(tr.D.parameters())):
+        assert torch.equal(a, b.detach()), 'graph warm-up / lr=0 replay changed the weights'
+    assert float(tr.pl_mean) != 0.0
+    graph_grads = {}
+    for name in ('Gmain', 'Dmain', 'Dreg', 'Greg'):
+        mod = tr.G if name.startswith('G') else tr.D
+        grads = tr._graphs['graphs'][name][4]
+        graph_grads[name] = [g.detach().clone() for g in grads]
+        for p, g in zip(mod.parameters(), grads):
+            p.grad = g
+        _check(z, name, name[0] + '.', mod, m['tol1'] if name.endswith('main') else m['tol2'])
+    # (b) eager launches of the same phases on the same state
+    tr.pl_mean.zero_()
+    for ph in tr.phases:
+        tr._phase_grads(ph, real, zz)
+        eager = [p.grad.detach().clone() for p in ph['module'].parameters()]
+        for ge, gg in zip(eager, graph_grads[ph['name']]):
+            scale = max(float(ge.abs().max()), 1e-20)
+            assert float((ge - gg).abs().max()) <= 1e-4 * scale + 1e-12, f"{ph['name']}: graph replay differs from eager launch"
 
 
 @pytest.mark.gpu
@@ -214,3 +250,59 @@ def test_multi_tensor_nan_to_num():
     nan_to_num_(ts, nan=0, posinf=1e5, neginf=-1e5)
     for a, b in zip(ts, want):
         assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('mode', ['strict', 'tf32'])
+def test_config_A_real_size_against_oracle(mode):
+    """BASELINE configs[0] at its real size (sg2ada.yaml, 64x64, batch 8, 512-channel layers, D 'orig', mbstd over the whole
+    batch): G forward, D forward and the parameter gradients of Gmain / Dmain / Dreg (R1) on the GPU against the CPU
+    oracle (oracle/ref_networks.py, pinned to the reference by net_tiny.npz) with the same weights and inputs."""
+    from sgb200 import training
+    tf32 = mode == 'tf32'
+    tol1, tol2 = (1e-2, 1e-2) if tf32 else (2e-4, 5e-4)
+    torch.backends.cudnn.allow_tf32 = tf32
+    cfg = training.config_sg2ada64(noise_mode='const', use_ema=False)
+    torch.manual_seed(0)
+    tr = training.Trainer(cfg, DEV)
+    with torch.no_grad():
+        for n_, p in tr.G.named_parameters():
+            if n_.endswith('noise_strength'):
+                p.fill_(0.1)
+    ocfg = RN.NetConfig(img_resolution=64, z_dim=512, w_dim=512, channel_base=32768, channel_max=512, map_layers=2, num_fp16_res=0,
+                        conv_clamp=None, d_arch='orig', mbstd_group_size=32)
+    GP = {k: v.detach().cpu().clone() for k, v in tr.G.state_dict().items()}
+    DP = {k: v.detach().cpu().clone() for k, v in tr.D.state_dict().items()}
+    g = torch.Generator().manual_seed(5)
+    zz = torch.randn(8, 512, generator=g)
+    real = torch.rand(8, 3, 64, 64, generator=g) * 2 - 1
+    with torch.no_grad():
+        img = tr.G.synthesis(tr.G.mapping(zz.to(DEV), None, skip_w_avg_update=True), noise_mode='const')
+        logits = tr.D(img, None)
+        img_o = RN.g_synthesis(GP, RN.g_mapping(GP, zz, ocfg), ocfg, noise='const')
+        logits_o = RN.d_forward(DP, img_o, ocfg)
+    assert_close(img, img_o, 1e-2 if tf32 else 1e-4, 'img 64x64')
+    assert_close(logits, logits_o, 2e-2 if tf32 else 2e-4, 'logits 64x64')
+
+    def grads_gpu(name, fn):
+        mod = tr.G if name.startswith('G') else tr.D
+        for p in mod.parameters():
+            p.grad = None
+        mod.requires_grad_(True)
+        fn()
+        mod.requires_grad_(False)
+        return {k: p.grad.detach().cpu() for k, p in mod.named_parameters() if p.grad is not None}
+
+    def compare(name, got, want, tol):
+        floor = 1e-2 * max(float(v.abs().max()) for v in want.values())
+        assert set(got) == set(want), (name, set(got) ^ set(want))
+        for k in want:
+            err = float((got[k].double() - want[k].double()).abs().max()) / max(float(want[k].abs().max()), floor)
+            assert err <= tol, f'{name} {k}: rel err {err:.3e} > {tol:.1e}'
+
+    go = RN.phase_gmain(GP, DP, zz, ocfg, ocfg, noise='const')[1]
+    compare('Gmain', grads_gpu('Gmain', lambda: tr.phase_Gmain(zz.to(DEV), 1)), go, tol1)
+    do = RN.phase_dmain(GP, DP, zz, real, ocfg, ocfg, noise='const')[1]
+    compare('Dmain', grads_gpu('Dmain', lambda: tr.phase_Dmain(zz.to(DEV), real.to(DEV), 1)), do, tol1)
+    ro = RN.phase_dreg(DP, real, ocfg, r1_gamma=cfg.r1_gamma, gain=4)[1]
+    compare('Dreg', grads_gpu('Dreg', lambda: tr.phase_Dreg(real.to(DEV), 4)), ro, tol2)
