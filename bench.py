@@ -131,26 +131,38 @@ def cpu_iteration_rate(cfg, batch, reps=1):
 
 
 def run_reference_arm(args):
+    """bench.py --impl reference: the reference's own CPU implementation of the path (its train_parts modules from the
+    snapshot baseline/_ref on CPU tensors => impl='ref' ops + F.conv2d) on the box's host cores, all threads; each step is a
+    bounded sample of the workload (every phase once at a reduced batch, combined with the lazy-regularisation weights)."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)          # torchrun exports OMP_NUM_THREADS=1: use every host core regardless
     cfg = workload_config(args.workload)
-    cores = torch.get_num_threads()
     sample_batch = 2 if cfg.img_resolution <= 256 else 1
-    vals = []
-    for i in range(args.warmup + args.steps):
-        if i < min(args.warmup, 1) or i >= args.warmup:     # one warm-up sample is enough on the CPU
-            v, _ = cpu_iteration_rate(cfg, sample_batch)
-            if i >= args.warmup:
-                vals.append(v)
+    kind = 'reference'
+    try:
+        from benchmarks import ref_harness
+        if ref_harness.reference_root() is None:
+            raise RuntimeError('no snapshot')
+        fn = lambda: ref_harness.cpu_phase_rate(args.workload, sample_batch)[0]     # noqa: E731
+        fn()
+        arm = "reference train_parts modules (baseline/_ref snapshot), impl='ref' path on host CPU"
+    except Exception:
+        kind = 'port'
+        fn = lambda: cpu_iteration_rate(cfg, sample_batch)[0]                        # noqa: E731
+        fn()
+        arm = 'oracle port of the reference impl=ref path on host CPU (reference snapshot not available)'
+    vals = [fn() for _ in range(args.steps)]        # the call above was the warm-up sample (one is enough on the CPU)
     value = statistics.mean(vals)
     sample = (f'{args.steps} x (Gmain + Dmain + Dreg + Greg once each at batch {sample_batch}, combined as '
-              f'Gmain+Dmain+Dreg/{cfg.d_reg_interval}+Greg/{cfg.g_reg_interval}), fp32')
+              f'Gmain+Dmain+Dreg/{cfg.d_reg_interval}+Greg/{cfg.g_reg_interval}), fp32, {cores} threads')
     line = dict(impl='reference', metric='train img/s (G+D)', value=value, unit='img/s', n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1000.0 * sample_batch / value, higher_is_better=True, scaling='weak',
                 vs_baseline=None, dtype='f32', data='synthetic',
-                config=dict(workload=WORKLOAD_DESC[args.workload], arm='oracle port of the reference impl=ref path on host CPU'),
-                cpu_baseline=dict(value=value, unit='img/s', cores=cores, kind='port', sample=sample),
+                config=dict(workload=WORKLOAD_DESC[args.workload], arm=arm, sample_batch=sample_batch),
+                cpu_baseline=dict(value=value, unit='img/s', cores=cores, kind=kind, sample=sample),
                 e2e=dict(value=value, unit='img/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
 
@@ -171,13 +183,19 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-roofline', action='store_true', help='skip the eager per-kernel timing loop (ncu launch-list runs)')
     ap.add_argument('--breakdown', default=None, help='write the per-kernel-family time table (json) here')
+    ap.add_argument('--no-secondary', action='store_true', help='skip the config-f 1024^2 run reported as `secondary`')
+    ap.add_argument('--no-strict', action='store_true', help='skip the strict-fp32 (reference default arithmetic) run')
+    ap.add_argument('--no-callers', action='store_true', help="skip the runs of the reference's unchanged callers (sgb200 / reference GPU path)")
+    ap.add_argument('--lean', action='store_true', help='only the headline measurement (ncu launch-list runs)')
     args = ap.parse_args()
 
+    if args.lean:
+        args.no_secondary = args.no_strict = args.no_callers = args.no_cpu_baseline = args.no_e2e = args.no_roofline = True
     if args.impl == 'reference':
         run_reference_arm(args)
         return
 
-    from sgb200 import training, _lib
+    from sgb200 import _lib
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -189,11 +207,91 @@ def main():
         dist.init_process_group('nccl', device_id=device)
     assert world == args.gpus or world == 1, f'--gpus {args.gpus} but WORLD_SIZE={world}'
     _lib.lib()     # fail loudly if the CUDA library is missing
-
     torch.backends.cudnn.benchmark = False
-    torch.backends.cudnn.allow_tf32 = (args.fp32_mode == 'tf32')
-    torch.backends.cuda.matmul.allow_tf32 = (args.fp32_mode == 'tf32')
-    cfg = workload_config(args.workload, cuda_graphs=not args.no_graphs)
+    ctx = dict(world=world, rank=rank, local_rank=local_rank, device=device, peaks=load_peaks())
+
+    # 1) the headline: BASELINE.json configs[1] (or --workload), fp32 tensors on the arithmetic --fp32-mode names
+    main_m = measure(ctx, args, args.workload, args.fp32_mode, args.steps, e2e=not args.no_e2e, roofline=not args.no_roofline,
+                     clocks=True, breakdown=args.breakdown)
+    # 2) config C on the same record: config-f 1024^2, 4 img/GPU, fp16 top-4 resolutions, one lazy-regularisation period
+    secondary = None
+    if not args.no_secondary and args.workload != 'f1024':
+        m = measure(ctx, args, 'f1024', args.fp32_mode, 16, e2e=not args.no_e2e, roofline=not args.no_roofline, clocks=False,
+                    breakdown=(args.breakdown + '.f1024.json') if args.breakdown else None)
+        if rank == 0:
+            secondary = dict(workload=WORKLOAD_DESC['f1024'], metric='train img/s (G+D)', value=m['value'], unit='img/s',
+                             ms_per_step=m['ms_per_step'], steps=16, batch_per_gpu=m['batch'], n_gpus=world, dtype=m['dtype'],
+                             gpu_launches=m['launches'], e2e=m['e2e'], roofline=m['roofline'], families=m['families'])
+    # 3) the reference-default arithmetic (perf.allow_tf32 = False): strict fp32 on the FFMA kernels, same workload
+    strict = None
+    if not args.no_strict and args.fp32_mode != 'strict' and world == 1:
+        m = measure(ctx, args, args.workload, 'strict', min(args.steps, 16), e2e=False, roofline=False, clocks=False)
+        strict = dict(value=m['value'], unit='img/s', ms_per_step=m['ms_per_step'], steps=min(args.steps, 16), dtype='f32',
+                      note='torch.backends.cudnn.allow_tf32=False (reference default, arguments.py:78): fp32 FFMA convolution kernels')
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # 4) the reference's UNCHANGED callers (train_parts G / D / SG2Loss / R1reg / PPLreg from baseline/_ref): on the sgb200
+    #    kernels through sgb200.install(), and on the reference's own CUDA path (its JIT plugins + cuDNN) = the kernel to beat
+    callers = vs_ref_gpu = None
+    if not args.no_callers and world == 1:
+        callers = run_ref_harness('sgb200', args.workload, args.fp32_mode)
+        ref_gpu = run_ref_harness('reference', args.workload, args.fp32_mode)
+        if isinstance(ref_gpu, dict) and 'img_per_s' in ref_gpu:
+            vs_ref_gpu = dict(reference_gpu_img_per_s=ref_gpu['img_per_s'], reference_gpu_ms_per_step=ref_gpu['ms_per_step'],
+                              ratio_value=main_m['value'] / ref_gpu['img_per_s'],
+                              ratio_unchanged_callers=(callers['img_per_s'] / ref_gpu['img_per_s']) if isinstance(callers, dict) and 'img_per_s' in callers else None,
+                              what="reference's own CUDA path on this GPU: bias_act_plugin / upfirdn2d_plugin (custom_ops.py JIT, sm_100a) + "
+                                   "cuDNN via F.conv2d, eager launches, cudnn.benchmark=True, same workload / batch / fp32 mode")
+        else:
+            vs_ref_gpu = ref_gpu
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        cpu = cpu_baseline(args.workload)
+
+    cfg = main_m['cfg']
+    line = dict(metric='train img/s (G+D)', value=main_m['value'], unit='img/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                ms_per_step=main_m['ms_per_step'], higher_is_better=True, scaling='weak', vs_baseline=None, dtype=main_m['dtype'],
+                data='synthetic',
+                config=dict(workload=WORKLOAD_DESC[args.workload], batch_per_gpu=main_m['batch'], global_batch=main_m['batch'] * world,
+                            resolution=cfg.img_resolution, parallelism=f'dp{world}', g_reg_interval=cfg.g_reg_interval,
+                            d_reg_interval=cfg.d_reg_interval, layout='channels_last' if cfg.channels_last else 'nchw',
+                            fp32_mode=args.fp32_mode, launch='eager' if args.no_graphs else 'cuda graphs (one per training phase)',
+                            l2='working set per step (activations, GBs) far exceeds the 126 MB L2; no explicit flush'),
+                gpu_launches=int(main_m['launches']), e2e=main_m['e2e'], roofline=main_m['roofline'], families=main_m['families'],
+                cpu_baseline=cpu, clocks=main_m['clocks'], secondary=secondary, strict_fp32=strict, callers_reference=callers,
+                vs_reference_gpu=vs_ref_gpu)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_ref_harness(backend, workload, fp32_mode, steps=16, timeout=420):
+    """benchmarks/ref_harness.py in its own process (the two backends bind the same module names) -> its JSON line."""
+    cmd = [sys.executable, os.path.join(ROOT, 'benchmarks', 'ref_harness.py'), '--backend', backend, '--workload', workload,
+           '--fp32-mode', fp32_mode, '--steps', str(steps), '--warmup', '3']
+    if backend == 'reference':
+        cmd.append('--cudnn-benchmark')
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith('{'):
+                return json.loads(ln)
+        return dict(unavailable=(r.stderr.strip().splitlines() or ['no output'])[-1][:300])
+    except Exception as e:     # missing snapshot, plugin build failure, time-out: report, never fail the bench
+        return dict(unavailable=f'{type(e).__name__}: {e}'[:300])
+
+
+def measure(ctx, args, workload, fp32_mode, steps, e2e, roofline, clocks, breakdown=None):
+    """One workload on this rank's GPU: W warm-up iterations, exactly `steps` timed iterations (barrier + synchronize on both
+    sides, max over ranks), optionally the end-to-end loop and the per-kernel-family eager loop."""
+    from sgb200 import training, _lib
+    world, rank, device, peaks = ctx['world'], ctx['rank'], ctx['device'], ctx['peaks']
+    torch.backends.cudnn.allow_tf32 = (fp32_mode == 'tf32')
+    torch.backends.cuda.matmul.allow_tf32 = (fp32_mode == 'tf32')
+    cfg = workload_config(workload, cuda_graphs=not args.no_graphs)
     tr = training.Trainer(cfg, device, rank=rank, world_size=world)
     R, N = cfg.img_resolution, cfg.batch_gpu
     host_real = torch.randint(0, 256, [N, cfg.img_channels, R, R], dtype=torch.uint8).pin_memory()
@@ -204,7 +302,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(device)
 
-    def timed_loop(steps, from_host, profile):
+    def timed_loop(nsteps, from_host, profile):
         """returns (ms max over ranks, launches, profile summary or None, last losses)"""
         tr.batch_idx = 0
         barrier()
@@ -216,7 +314,7 @@ def main():
         last = None
         nvtx_id = torch.cuda.nvtx.range_start('sgb_timed')   # process-wide range (backward kernels launch from autograd's
                                                               # thread): ncu --nvtx --nvtx-include "sgb_timed" profiles this loop only
-        for _ in range(steps):
+        for _ in range(nsteps):
             real = host_real.to(device, non_blocking=True) if from_host else dev_real
             out = tr.iteration(real, eager=profile)      # per-launch events need eager launches
             if from_host:
@@ -227,7 +325,8 @@ def main():
         barrier()
         ms = e0.elapsed_time(e1)
         launches = _lib.launch_count() + tr.replayed_launches - n0
-        summ = _lib.profile_stop().summary() if profile else None
+        prof = _lib.profile_stop() if profile else None
+        summ = (prof.summary(), prof.summary(by_tag=True)) if profile else None
         if world > 1:
             t = torch.tensor([ms], device=device, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -238,83 +337,100 @@ def main():
     for i in range(max(args.warmup, 3)):
         tr.iteration(dev_real, force_all_phases=(i == 0))
     barrier()
-
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(ctx['local_rank']) if (rank == 0 and clocks) else None
     if sampler:
         sampler.start()
-    ms, launches, _, _ = timed_loop(args.steps, from_host=False, profile=False)
-    clocks = sampler.stop() if sampler else None
+    ms, launches, _, _ = timed_loop(steps, from_host=False, profile=False)
+    clk = sampler.stop() if sampler else None
     # per-kernel-family device time (roofline leg): the same K steps launched eagerly with CUDA events around
     # every libsgb200 launch; not part of the reported step time
     summ = None
-    if not args.no_roofline:
-        _, _, summ, _ = timed_loop(args.steps, from_host=False, profile=True)
+    if roofline:
+        _, _, summ, _ = timed_loop(steps, from_host=False, profile=True)
+        summ, by_tag = summ
+    e2e_d = None
+    if e2e:
+        ms_e, _, _, last = timed_loop(steps, from_host=True, profile=False)
+        e2e_d = dict(value=steps * N * world / (ms_e / 1000.0), unit='img/s', h2d_bytes_per_step=host_real.numel(),
+                     d2h_bytes_per_step=4 * len(last or {}), ms_per_step=ms_e / steps)
+    out = dict(cfg=cfg, batch=N, value=steps * N * world / (ms / 1000.0), ms_per_step=ms / steps, launches=int(launches), e2e=e2e_d,
+               clocks=clk, roofline=None, families=None,
+               dtype=('tf32' if fp32_mode == 'tf32' else 'f32') + ('' if cfg.num_fp16_res == 0 else '+f16'))
+    if rank == 0 and summ:
+        out['roofline'], out['families'] = roofline_of(summ, cfg, workload, fp32_mode, peaks, steps)
+        if breakdown:
+            os.makedirs(os.path.dirname(os.path.abspath(breakdown)), exist_ok=True)
+            with open(breakdown, 'w') as f:
+                json.dump(dict(step_ms=ms / steps, kernel_ms_per_step={k: v['ms'] / steps for k, v in summ.items()}, detail=summ,
+                               by_shape=by_tag), f, indent=1)
+    del tr
+    torch.cuda.empty_cache()
+    return out
 
-    e2e = None
-    if not args.no_e2e:
-        ms_e, _, _, last = timed_loop(args.steps, from_host=True, profile=False)
-        e2e = dict(value=args.steps * N * world / (ms_e / 1000.0), unit='img/s', h2d_bytes_per_step=host_real.numel(),
-                   d2h_bytes_per_step=4 * len(last or {}), ms_per_step=ms_e / args.steps)
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    peaks = load_peaks()
-    value = args.steps * N * world / (ms / 1000.0)
-    # dominant kernel family by device time (eager loop, CUDA events around every libsgb200 launch)
-    roof = None
+def roofline_of(summ, cfg, workload, fp32_mode, peaks, steps):
+    """(roofline object of the dominant kernel family, {family: ms per step / achieved / fraction}) from the CUDA-event summary.
+    Tensor peaks: MEASURED_PEAKS.json has the bf16 rate only; fp16 MMAs run at the bf16 rate and kind::tf32 MMAs at half of it
+    (tcgen05 K = 8 per instruction instead of 16), so fp32 tensors are reported against bf16 sustained / 2.  Mixed workloads
+    (f1024: fp32 below 128^2, fp16 above) are reported against the fp16 rate, the stricter denominator."""
     traffic = {}
     tpath = os.path.join(ROOT, 'profiles', 'r1_conv_traffic.json')        # DRAM bytes per launch from ncu (profiles/README.md)
-    if os.path.exists(tpath) and args.workload == 'ffhq256':
+    if os.path.exists(tpath) and workload == 'ffhq256':
         with open(tpath) as f:
             traffic = json.load(f)
-    if summ:
-        total_ms = sum(d['ms'] for d in summ.values()) or 1.0
-        dom = max(summ, key=lambda k: summ[k]['ms'])
-        d = summ[dom]
-        if dom.startswith('conv'):
-            # fp32 tensors run TF32 MMAs (half the bf16 rate) in the forward / data-gradient kernels
-            tf32 = cfg.num_fp16_res == 0 and args.fp32_mode == 'tf32' and dom.startswith('conv_fwd')
-            peak = peaks['tc_sustained'] / (2 if tf32 else 1)
-            ach = d['flops'] / (d['ms'] / 1000.0) / 1e12
-            roof = dict(kernel=dom, bound='tensor', achieved=ach, peak=peak, unit='TFLOP/s', frac=ach / peak,
-                        traffic=(traffic.get(dom) or {}).get('dram_bytes_per_launch'),
-                        peak_source=peaks['source'] + (' bf16 sustained / 2 (TF32 MMA rate)' if tf32 else ' bf16 sustained'),
-                        launches=d['launches'], avg_launch_ms=d['ms'] / d['launches'], share_of_kernel_time=d['ms'] / total_ms,
-                        algorithmic_flops_per_launch=d['flops'] / d['launches'])
-        else:
-            ach = d['bytes'] / (d['ms'] / 1000.0) / 1e9
-            roof = dict(kernel=dom, bound='hbm', achieved=ach, peak=peaks['hbm'], unit='GB/s', frac=ach / peaks['hbm'], traffic=None,
-                        peak_source=peaks['source'], launches=d['launches'], avg_launch_ms=d['ms'] / d['launches'],
-                        share_of_kernel_time=d['ms'] / total_ms, algorithmic_bytes_per_launch=d['bytes'] / d['launches'])
-        if args.breakdown:
-            os.makedirs(os.path.dirname(os.path.abspath(args.breakdown)), exist_ok=True)
-            with open(args.breakdown, 'w') as f:
-                json.dump(dict(step_ms=ms / args.steps, kernel_ms_per_step={k: v['ms'] / args.steps for k, v in summ.items()},
-                               detail=summ), f, indent=1)
+    total_ms = sum(d['ms'] for d in summ.values()) or 1.0
+    tf32 = cfg.num_fp16_res == 0 and fp32_mode == 'tf32'
+    tc_peak = peaks['tc_sustained'] / (2 if tf32 else 1)
+    fam = {}
+    for k, d in summ.items():
+        e = dict(ms_per_step=d['ms'] / steps, launches_per_step=d['launches'] / steps)
+        if k.startswith('conv') and d['flops'] > 0:
+            e['tflops'] = d['flops'] / (d['ms'] / 1000.0) / 1e12
+            e['frac_tensor'] = e['tflops'] / tc_peak
+        if d['bytes'] > 0:
+            e['gbs'] = d['bytes'] / (d['ms'] / 1000.0) / 1e9
+            e['frac_hbm'] = e['gbs'] / peaks['hbm']
+        fam[k] = e
+    dom = max(summ, key=lambda k: summ[k]['ms'])
+    d = summ[dom]
+    if dom.startswith('conv'):
+        ach = d['flops'] / (d['ms'] / 1000.0) / 1e12
+        roof = dict(kernel=dom, bound='tensor', achieved=ach, peak=tc_peak, unit='TFLOP/s', frac=ach / tc_peak,
+                    traffic=(traffic.get(dom) or {}).get('dram_bytes_per_launch'),
+                    peak_source=peaks['source'] + (' bf16 sustained / 2 (TF32 MMA rate)' if tf32 else ' bf16 sustained (= fp16 MMA rate)'),
+                    launches=d['launches'], avg_launch_ms=d['ms'] / d['launches'], share_of_kernel_time=d['ms'] / total_ms,
+                    algorithmic_flops_per_launch=d['flops'] / d['launches'],
+                    hbm_view=dict(gbs=d['bytes'] / (d['ms'] / 1000.0) / 1e9, frac=d['bytes'] / (d['ms'] / 1000.0) / 1e9 / peaks['hbm']))
+    else:
+        ach = d['bytes'] / (d['ms'] / 1000.0) / 1e9
+        roof = dict(kernel=dom, bound='hbm', achieved=ach, peak=peaks['hbm'], unit='GB/s', frac=ach / peaks['hbm'], traffic=None,
+                    peak_source=peaks['source'], launches=d['launches'], avg_launch_ms=d['ms'] / d['launches'],
+                    share_of_kernel_time=d['ms'] / total_ms, algorithmic_bytes_per_launch=d['bytes'] / d['launches'])
+    return roof, fam
 
-    cpu = None
-    if not args.no_cpu_baseline and world == 1:
-        sb = 8 if R <= 256 else 1            # ~10-30 s of CPU work on the box's host cores
+
+def cpu_baseline(workload):
+    """The reference's own modules (baseline/_ref, impl='ref' on CPU tensors) on this box's host cores, all threads, on a
+    bounded sample: every phase once at a reduced batch, combined with the lazy-regularisation weights.  Falls back to the
+    oracle port (pinned to the reference by tests/golden) when the snapshot is absent."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    R = {'ffhq256': 256, 'f1024': 1024, 'sg2ada64': 64}[workload]
+    sb = 8 if R <= 256 else 1
+    try:
+        from benchmarks import ref_harness
+        if ref_harness.reference_root() is None:
+            raise RuntimeError('no snapshot')
+        v, t, gi, di = ref_harness.cpu_phase_rate(workload, sb)
+        return dict(value=v, unit='img/s', cores=cores, kind='reference',
+                    sample=f"reference train_parts G/D + SG2Loss/R1reg/PPLreg (baseline/_ref, impl='ref'), Gmain+Dmain+Dreg/{di}+Greg/{gi} "
+                           f'once each at batch {sb}, fp32 ({sum(t.values()):.1f} s of CPU work)')
+    except Exception as e:
+        cfg = workload_config(workload)
         v, t = cpu_iteration_rate(cfg, sb)
-        cpu = dict(value=v, unit='img/s', cores=torch.get_num_threads(), kind='port',
-                   sample=f'Gmain+Dmain+Dreg/{cfg.d_reg_interval}+Greg/{cfg.g_reg_interval} once each at batch {sb}, fp32 '
-                          f'({sum(t.values()):.1f} s of CPU work)')
-
-    line = dict(metric='train img/s (G+D)', value=value, unit='img/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
-                ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
-                dtype=('tf32' if args.fp32_mode == 'tf32' else 'f32') + ('' if cfg.num_fp16_res == 0 else '+f16'), data='synthetic',
-                config=dict(workload=WORKLOAD_DESC[args.workload], batch_per_gpu=N, global_batch=N * world, resolution=R,
-                            parallelism=f'dp{world}', g_reg_interval=cfg.g_reg_interval, d_reg_interval=cfg.d_reg_interval,
-                            layout='channels_last' if cfg.channels_last else 'nchw', fp32_mode=args.fp32_mode,
-                            launch='eager' if args.no_graphs else 'cuda graphs (one per training phase)',
-                            l2='working set per step (activations, GBs) far exceeds the 126 MB L2; no explicit flush'),
-                gpu_launches=int(launches), e2e=e2e, roofline=roof, cpu_baseline=cpu, clocks=clocks)
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+        return dict(value=v, unit='img/s', cores=cores, kind='port',
+                    sample=f'oracle port ({type(e).__name__}: reference snapshot unusable), Gmain+Dmain+Dreg/{cfg.d_reg_interval}+'
+                           f'Greg/{cfg.g_reg_interval} once each at batch {sb}, fp32 ({sum(t.values()):.1f} s of CPU work)')
 
 
 if __name__ == '__main__':

@@ -24,6 +24,9 @@ import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if os.path.realpath('/root/repo') == os.path.realpath(ROOT):
+    ROOT = '/root/repo'       # same path in the authoring container and on the GPU box (a symlink there): the plugin build
+                              # directory prepared by build() is then found again, not rebuilt
 _backend = None
 
 
@@ -60,7 +63,32 @@ def _shims():
         collections.MutableMapping = collections.abc.MutableMapping
 
 
-def import_reference(backend):
+def _plugin_import_shim():
+    """The reference's custom_ops.get_plugin (custom_ops.py:109-111) builds a plugin with torch.utils.cpp_extension.load and then
+    calls importlib.import_module(name).  torch 1.7 registered the built module in sys.modules; torch 2.x does not, so on this
+    image the import raises, the op prints "Failed!" and silently falls back to its slow impl='ref' path -- which would make
+    the reference's GPU numbers meaningless as "the kernel to beat".  Register the module the way torch 1.7 did."""
+    import torch.utils.cpp_extension as ce
+    if getattr(ce.load, '_sgb_shim', False):
+        return
+    orig = ce.load
+
+    def load(name, *a, **k):
+        mod = orig(name, *a, **k)
+        if isinstance(mod, types.ModuleType):
+            sys.modules.setdefault(name, mod)
+        return mod
+    load._sgb_shim = True
+    ce.load = load
+
+
+def plugin_status():
+    """{'bias_act': True/False, 'upfirdn2d': True/False}: did the reference's CUDA plugins load (backend='reference')?"""
+    from stylegan2ada.torch_utils.ops import bias_act as rb, upfirdn2d as ru
+    return dict(bias_act=bool(rb._init()), upfirdn2d=bool(ru._init()))
+
+
+def import_reference(backend, repair_plugins=True):
     """Put the snapshot on sys.path (and sgb200 in front of it for backend='sgb200').  Returns the root."""
     global _backend
     assert backend in ('sgb200', 'reference')
@@ -84,6 +112,8 @@ def import_reference(backend):
         # build made in one gpurun call is found again and this container's ~/.cache is not involved
         os.environ.setdefault('TORCH_EXTENSIONS_DIR', os.path.join(root, '_torch_extensions'))
         os.environ.setdefault('TORCH_CUDA_ARCH_LIST', '10.0a')
+        if repair_plugins:
+            _plugin_import_shim()
     _backend = backend
     return root
 
@@ -243,6 +273,26 @@ def time_iterations(tr, steps, warmup, device):
     return (time.perf_counter() - t0) * 1000.0 / steps
 
 
+def cpu_phase_rate(workload, batch, g_reg_interval=16, d_reg_interval=4):
+    """CPU baseline sample: the reference's own phases (impl='ref' ops, F.conv2d) once each at per-step batch `batch`
+    (Greg on batch // 2, regularizations.py:22), combined into the amortised iteration Gmain + Dmain + Dreg/di + Greg/gi.
+    Returns (img/s, {phase: seconds}, gi, di)."""
+    import time
+    tr = RefCallerTrainer(workload, 'cpu', 'reference', use_ema=False, g_reg_interval=g_reg_interval, d_reg_interval=d_reg_interval,
+                          batch_gpu=batch, mbstd=min(WORKLOADS[workload]['mbstd'], batch))
+    w = tr.w
+    g = torch.Generator().manual_seed(2)
+    z = torch.randn(batch, w['z_dim'], generator=g)
+    real = torch.rand(batch, 3, w['res'], w['res'], generator=g) * 2 - 1
+    t = dict(Gmain=0.0, Dmain=0.0, Greg=0.0, Dreg=0.0)
+    for ph in tr.phases:
+        t0 = time.perf_counter()
+        tr.phase_grads(ph.name, real, z, ph.interval)
+        t[ph.name] = time.perf_counter() - t0
+    per_iter = t['Gmain'] + t['Dmain'] + t['Dreg'] / d_reg_interval + t['Greg'] / g_reg_interval
+    return batch / per_iter, t, g_reg_interval, d_reg_interval
+
+
 def main():
     """python benchmarks/ref_harness.py --backend sgb200|reference --workload ffhq256 [--tf32] -> one JSON line"""
     import argparse
@@ -256,7 +306,11 @@ def main():
     ap.add_argument('--fp32-mode', default='tf32', choices=['tf32', 'strict'])
     ap.add_argument('--batch', type=int, default=None)
     ap.add_argument('--cudnn-benchmark', action='store_true')
+    ap.add_argument('--as-is', action='store_true', help="backend=reference without the plugin import repair: what the unmodified "
+                    "reference does on torch 2.x (plugins fail to import, ops fall back to impl='ref')")
     a = ap.parse_args()
+    if a.backend == 'reference':
+        import_reference('reference', repair_plugins=not a.as_is)
     tf32 = a.fp32_mode == 'tf32'
     torch.backends.cudnn.allow_tf32 = tf32             # trainers.py:510-511 (perf.allow_tf32)
     torch.backends.cuda.matmul.allow_tf32 = tf32
@@ -267,9 +321,10 @@ def main():
     tr = RefCallerTrainer(a.workload, a.device, a.backend, **over)
     ms = time_iterations(tr, a.steps, a.warmup, a.device)
     n = tr.w['batch_gpu']
+    plugins = plugin_status() if (a.backend == 'reference' and a.device != 'cpu') else None
     print(json.dumps(dict(callers='reference (unchanged train_parts)', backend=a.backend, device=a.device, workload=a.workload,
                           batch_gpu=n, fp32_mode=a.fp32_mode, steps=a.steps, ms_per_step=ms, img_per_s=1000.0 * n / ms,
-                          cudnn_benchmark=a.cudnn_benchmark, threads=torch.get_num_threads())), flush=True)
+                          cudnn_benchmark=a.cudnn_benchmark, threads=torch.get_num_threads(), reference_cuda_plugins=plugins)), flush=True)
 
 
 if __name__ == '__main__':

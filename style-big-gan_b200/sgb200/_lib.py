@@ -132,13 +132,13 @@ def out_format(t):
 # ---- optional per-launch timing (bench.py's roofline leg): CUDA events on the launching stream ----------
 class _Profile:
     def __init__(self):
-        self.records = []          # (kind, start_event, end_event, flops, bytes)
+        self.records = []          # (kind, start_event, end_event, flops, bytes, tag)
 
-    def summary(self):
-        """kind -> dict(launches, ms, flops, bytes); call after torch.cuda.synchronize()."""
+    def summary(self, by_tag=False):
+        """kind (or "kind | tag" with by_tag) -> dict(launches, ms, flops, bytes); call after torch.cuda.synchronize()."""
         out = {}
-        for kind, e0, e1, fl, by in self.records:
-            d = out.setdefault(kind, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+        for kind, e0, e1, fl, by, tag in self.records:
+            d = out.setdefault(f'{kind} | {tag}' if (by_tag and tag) else kind, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
             d['launches'] += 1
             d['ms'] += e0.elapsed_time(e1)
             d['flops'] += fl
@@ -163,10 +163,10 @@ def profile_stop():
 
 class prof:
     """`with prof(kind, flops, bytes):` around ONE kernel launch; free when profiling is off."""
-    __slots__ = ('kind', 'flops', 'bytes', 'e0')
+    __slots__ = ('kind', 'flops', 'bytes', 'e0', 'tag')
 
-    def __init__(self, kind, flops=0.0, nbytes=0.0):
-        self.kind, self.flops, self.bytes = kind, flops, nbytes
+    def __init__(self, kind, flops=0.0, nbytes=0.0, tag=None):
+        self.kind, self.flops, self.bytes, self.tag = kind, flops, nbytes, tag
 
     def __enter__(self):
         if PROFILE is not None:
@@ -178,5 +178,5 @@ class prof:
         if PROFILE is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            PROFILE.records.append((self.kind, self.e0, e1, float(self.flops), float(self.bytes)))
+            PROFILE.records.append((self.kind, self.e0, e1, float(self.flops), float(self.bytes), self.tag))
         return False

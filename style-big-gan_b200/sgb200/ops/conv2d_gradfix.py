@@ -232,7 +232,9 @@ def _conv2d_op(transpose, weight_shape, stride, padding, output_padding, dilatio
                 nbytes = (input.numel() + y.numel() + w.numel()) * input.element_size()
                 ws = _attach_workspace(d, input.device)
                 tc = _lib.lib().sgb_conv2d_uses_tensor_cores(d)
-                with torch.cuda.device(input.device), _lib.prof(('conv_fwd_simt', 'conv_fwd_tc', 'conv_fwd_small')[tc], flops, nbytes):
+                tag = (f"{str(input.dtype)[6:]} x[{input.shape[0]},{ci},{input.shape[2]},{input.shape[3]}] co{co} k{kh} s{s}"
+                       f"{' T' if transpose else ''}{' mod' if sc is not None else ''}") if _lib.PROFILE is not None else None
+                with torch.cuda.device(input.device), _lib.prof(('conv_fwd_simt', 'conv_fwd_tc', 'conv_fwd_small')[tc], flops, nbytes, tag):
                     rc = _lib.lib().sgb_conv2d_forward(d, _lib.ptr(x_), _lib.ptr(w), _lib.ptr(y), _lib.stream_ptr(input.device))
                 _lib.check(rc, 'conv2d_forward')
             ctx.save_for_backward(input, weight, in_scale)
@@ -309,7 +311,9 @@ def _conv2d_op(transpose, weight_shape, stride, padding, output_padding, dilatio
             dwf = torch.empty([dy_.shape[1], x_.shape[1] // groups, kh, kw], dtype=_lib.acc_dtype(input.dtype), device=input.device)
             nbytes += dwf.numel() * dwf.element_size()
             tc = _lib.lib().sgb_conv2d_wgrad_uses_tensor_cores(d)
-            with torch.cuda.device(input.device), _lib.prof('conv_wgrad_tc' if tc else 'conv_wgrad_simt', flops, nbytes):
+            tag = (f"{str(input.dtype)[6:]} x[{x_.shape[0]},{x_.shape[1]},{x_.shape[2]},{x_.shape[3]}] dy[{dy_.shape[1]},{dy_.shape[2]},"
+                   f"{dy_.shape[3]}] k{kh} s{s}") if _lib.PROFILE is not None else None
+            with torch.cuda.device(input.device), _lib.prof('conv_wgrad_tc' if tc else 'conv_wgrad_simt', flops, nbytes, tag):
                 rc = _lib.lib().sgb_conv2d_wgrad(d, _lib.ptr(x_), _lib.ptr(dy_), _lib.ptr(dwf), _lib.stream_ptr(input.device))
             _lib.check(rc, 'conv2d_wgrad')
             if padded:
