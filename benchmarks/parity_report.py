@@ -71,8 +71,57 @@ def worker(backend):
             res[phase] = dict(worst=errs[0][0], tensor=errs[0][1], median=errs[len(errs) // 2][0], n_over_1e2=sum(e > 1e-2 for e, _ in errs),
                               n=len(errs))
         out[mode] = res
-    print('PARITY_JSON ' + json.dumps(dict(backend=backend, result=out,
+    out_a = config_a(H, backend)
+    print('PARITY_JSON ' + json.dumps(dict(backend=backend, result=out, config_a=out_a,
                                             plugins=H.plugin_status() if backend == 'reference' else None)), flush=True)
+
+
+def config_a(H, backend):
+    """BASELINE configs[0] at its real size (sg2ada.yaml: 64x64, batch 8, 512 channels, D 'orig'): gradients of Gmain / Dmain /
+    Dreg from the unchanged callers on the GPU against the SAME reference modules run on the CPU in fp32 (impl='ref').  The
+    'reference' worker runs first, computes that CPU golden and leaves it in gpurun_out/ for the 'sgb200' worker (whose ops
+    refuse CPU tensors)."""
+    import numpy as np
+    import torch
+    path = os.path.join(ROOT, 'gpurun_out', 'parity_config_a_golden.npz')
+    g = torch.Generator().manual_seed(5)
+    zz = torch.randn(8, 512, generator=g)
+    real = torch.rand(8, 3, 64, 64, generator=g) * 2 - 1
+
+    def build(dev):
+        tr = H.RefCallerTrainer('sg2ada64', dev, backend, noise_mode='const', use_ema=False, seed=3)
+        with torch.no_grad():
+            for n_, p in tr.G.named_parameters():
+                if n_.endswith('noise_strength'):
+                    p.fill_(0.1)
+        return tr
+
+    def grads(tr, dev):
+        res = {}
+        for phase, gain in (('Gmain', 1), ('Dmain', 1), ('Dreg', 4)):
+            ph = tr.phase_grads(phase, real.to(dev), zz.to(dev), gain)
+            res[phase] = {k: p.grad.detach().double().cpu().numpy() for k, p in ph.module.named_parameters() if p.grad is not None}
+        return res
+
+    if backend == 'reference':
+        torch.backends.cudnn.allow_tf32 = False
+        gold = grads(build('cpu'), 'cpu')
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        np.savez(path, **{f'{ph}/{k}': v for ph, d in gold.items() for k, v in d.items()})
+    if not os.path.exists(path):
+        return None
+    z = np.load(path)
+    out = {}
+    for mode in ('strict', 'tf32'):
+        torch.backends.cudnn.allow_tf32 = mode == 'tf32'
+        got = grads(build('cuda'), 'cuda')
+        out[mode] = {}
+        for phase, d in got.items():
+            keys = [k for k in z.files if k.startswith(phase + '/')]
+            floor = 1e-2 * max(float(np.abs(z[k]).max()) for k in keys)
+            errs = sorted((float(np.abs(d[k.split('/', 1)[1]] - z[k]).max()) / max(float(np.abs(z[k]).max()), floor), k.split('/', 1)[1]) for k in keys)
+            out[mode][phase] = dict(worst=errs[-1][0], tensor=errs[-1][1], median=errs[len(errs) // 2][0])
+    return out
 
 
 def main():
@@ -84,7 +133,7 @@ def main():
         worker(a.worker)
         return
     rows = {}
-    for backend in ('sgb200', 'reference'):
+    for backend in ('reference', 'sgb200'):
         r = subprocess.run([sys.executable, os.path.abspath(__file__), '--worker', backend], capture_output=True, text=True, timeout=1500)
         line = [ln for ln in r.stdout.splitlines() if ln.startswith('PARITY_JSON ')]
         if not line:
@@ -98,6 +147,15 @@ def main():
             cells = []
             for backend in ('sgb200', 'reference'):
                 r = rows.get(backend, {}).get('result', {}).get(mode, {}).get(phase)
+                cells += [f"{r['worst']:.2e} ({r['tensor']})", f"{r['median']:.2e}"] if r else ['n/a', 'n/a']
+            lines.append(f'| {mode} | {phase} | ' + ' | '.join(cells) + ' |')
+    lines += ['', 'Config A at its real size (sg2ada.yaml 64x64, batch 8, 512 channels), golden = the same reference modules on the CPU (fp32):', '',
+              '| mode | phase | sgb200 worst (tensor) | sgb200 median | reference GPU path worst (tensor) | reference median |', '|---|---|---|---|---|---|']
+    for mode in ('strict', 'tf32'):
+        for phase in ('Gmain', 'Dmain', 'Dreg'):
+            cells = []
+            for backend in ('sgb200', 'reference'):
+                r = ((rows.get(backend, {}).get('config_a') or {}).get(mode) or {}).get(phase)
                 cells += [f"{r['worst']:.2e} ({r['tensor']})", f"{r['median']:.2e}"] if r else ['n/a', 'n/a']
             lines.append(f'| {mode} | {phase} | ' + ' | '.join(cells) + ' |')
     print('\n'.join(lines))

@@ -148,6 +148,58 @@ def main():
         return (lambda: modulated_conv2d(x, w, s, up=2, padding=1, resample_filter=f, flip_weight=False, fused_modconv=False)), \
             2.0 * 8 * 128 * 128 * 128 * 64 * 9, (x.numel() + 8 * 64 * 256 * 256) * 4
 
+    # config C (f1024) shapes: batch 4, fp16, few channels at 512^2 / 1024^2 (HBM-bound layers)
+    @case('fwd_f16_c32_1024')
+    def _():
+        x, w = conv_case(4, 32, 1024, torch.float16)
+        return (lambda: conv2d_gradfix.conv2d(x, w, padding=1)), 2.0 * 4 * 1024 * 1024 * 32 * 32 * 9, 2 * x.numel() * 2
+
+    @case('fwd_f16_c64_512')
+    def _():
+        x, w = conv_case(4, 64, 512, torch.float16)
+        return (lambda: conv2d_gradfix.conv2d(x, w, padding=1)), 2.0 * 4 * 512 * 512 * 64 * 64 * 9, 2 * x.numel() * 2
+
+    @case('fwd_f32_c64_256_n32')
+    def _():
+        x, w = conv_case(32, 64, 256, torch.float32)
+        return (lambda: conv2d_gradfix.conv2d(x, w, padding=1)), 2.0 * 32 * 256 * 256 * 64 * 64 * 9, 2 * x.numel() * 4
+
+    @case('wgrad_f16_c32_1024')
+    def _():
+        x, w = conv_case(4, 32, 1024, torch.float16)
+        w.requires_grad_(True)
+        y = conv2d_gradfix.conv2d(x, w, padding=1)
+        dy = torch.randn_like(y)
+        return (lambda: torch.autograd.grad(y, [w], dy, retain_graph=True)), 2.0 * 4 * 1024 * 1024 * 32 * 32 * 9, 2 * x.numel() * 2
+
+    @case('wgrad_f16_c64_512')
+    def _():
+        x, w = conv_case(4, 64, 512, torch.float16)
+        w.requires_grad_(True)
+        y = conv2d_gradfix.conv2d(x, w, padding=1)
+        dy = torch.randn_like(y)
+        return (lambda: torch.autograd.grad(y, [w], dy, retain_graph=True)), 2.0 * 4 * 512 * 512 * 64 * 64 * 9, 2 * x.numel() * 2
+
+    @case('fir_f16_c32_1024')
+    def _():
+        x = cl(torch.randn(4, 32, 1025, 1025, device=DEV, dtype=torch.float16))
+        return (lambda: upfirdn2d.upfirdn2d(x, f, padding=[1, 1, 1, 1], gain=4)), 0, 2 * x.numel() * 2
+
+    @case('fir_f32_c64_256')
+    def _():
+        x = cl(torch.randn(32, 64, 257, 257, device=DEV))
+        return (lambda: upfirdn2d.upfirdn2d(x, f, padding=[1, 1, 1, 1], gain=4)), 0, 2 * x.numel() * 4
+
+    @case('down2_f16_c32_1024')
+    def _():
+        x = cl(torch.randn(4, 32, 1024, 1024, device=DEV, dtype=torch.float16))
+        return (lambda: upfirdn2d.downsample2d(x, f)), 0, 1.25 * x.numel() * 2
+
+    @case('up2_f32_c64_128')
+    def _():
+        x = cl(torch.randn(32, 64, 128, 128, device=DEV))
+        return (lambda: upfirdn2d.upsample2d(x, f)), 0, 5 * x.numel() * 4
+
     names = list(cases) if args.cases == 'all' else args.cases.split(',')
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
     for name in names:

@@ -108,7 +108,8 @@ int sgb_conv2d_forward(const sgb_conv_desc* d, const void* x, const void* w, voi
 int sgb_conv2d_wgrad(const sgb_conv_desc* d, const void* x, const void* dy, void* dw, void* stream);
 
 /* Which kernel sgb_conv2d_forward will run for this descriptor, for reporting only: 1 = the tcgen05 (tensor-core)
- * implicit-GEMM kernels, 2 = the small-output-channel 1x1 bandwidth kernel (toRGB), 0 = the generic SIMT kernel. */
+ * implicit-GEMM kernels, 3 = the tcgen05 kernel whose activation patches are staged by TMA (cp.async.bulk.tensor),
+ * 2 = the small-output-channel 1x1 bandwidth kernel (toRGB), 0 = the generic SIMT kernel. */
 int sgb_conv2d_uses_tensor_cores(const sgb_conv_desc* d);
 /* same question for sgb_conv2d_wgrad: 0 = SIMT, non-zero = tensor cores; 2 = the halo-tile kernels, the only ones that
  * accept d->out_scale in a weight-gradient descriptor (there it is a per-sample scale [N, co] on dy: the style modulation

@@ -167,8 +167,13 @@ def _fc(x, w, b, act='linear', lr_mult=1.0):
     return R.bias_act(x.matmul(wg.t()), b, act=act)
 
 
+def _base(t):
+    """fp32 (the reference's type), or fp64 when the oracle is run in double to serve as an exact reference"""
+    return torch.float64 if t.dtype == torch.float64 else torch.float32
+
+
 def g_mapping(P, z, cfg):
-    x = z.to(torch.float32)
+    x = z.to(_base(z))
     x = x * (x.square().mean(dim=1, keepdim=True) + 1e-8).rsqrt()
     for i in range(cfg.map_layers):
         x = _fc(x, P[f'mapping.fc{i}.weight'], P[f'mapping.fc{i}.bias'], act='lrelu', lr_mult=0.01)
@@ -207,12 +212,12 @@ def _torgb(P, pre, x, w, cfg, fused_modconv=False):
 
 def g_synthesis(P, ws, cfg, noise='const', fused_modconv=False):
     """noise: 'const' | 'none' | dict(layer prefix -> [N,1,R,R] tensor)."""
-    ws = ws.to(torch.float32)
+    ws = ws.to(_base(ws))
     x = img = None
     widx = 0
     for res in cfg.g_resolutions:
         pre = f'synthesis.b{res}.'
-        dtype = torch.float16 if res >= cfg.fp16_resolution else torch.float32
+        dtype = torch.float16 if res >= cfg.fp16_resolution else ws.dtype       # ws.dtype: fp32, or fp64 for a double oracle run
         if res == 4:
             x = P[pre + 'const'].to(dtype).unsqueeze(0).repeat(ws.shape[0], 1, 1, 1)
             x = _synth_layer(P, pre + 'conv1.', x, ws[:, widx], cfg, 1, res, noise, fused_modconv=fused_modconv)
@@ -224,7 +229,7 @@ def g_synthesis(P, ws, cfg, noise='const', fused_modconv=False):
             nconv = 2
         if img is not None:
             img = R.upsample2d(img, _filt())
-        y = _torgb(P, pre + 'torgb.', x, ws[:, widx + nconv], cfg, fused_modconv=fused_modconv).to(torch.float32)
+        y = _torgb(P, pre + 'torgb.', x, ws[:, widx + nconv], cfg, fused_modconv=fused_modconv).to(ws.dtype)
         img = y if img is None else img + y
         widx += nconv
     return img
@@ -253,10 +258,11 @@ def _mbstd(x, group_size, nch):
 
 
 def d_forward(P, img, cfg):
+    base = _base(img)
     x = None
     for res in cfg.d_resolutions:
         pre = f'b{res}.'
-        dtype = torch.float16 if res >= cfg.fp16_resolution else torch.float32
+        dtype = torch.float16 if res >= cfg.fp16_resolution else base
         if x is not None:
             x = x.to(dtype)
         if res == cfg.img_resolution or cfg.d_arch == 'skip':
@@ -271,9 +277,9 @@ def d_forward(P, img, cfg):
         else:
             x = _conv_layer(P, pre + 'conv0.', x, act='lrelu', clamp=cfg.conv_clamp)
             x = _conv_layer(P, pre + 'conv1.', x, act='lrelu', down=2, clamp=cfg.conv_clamp)
-    x = x.to(torch.float32)
+    x = x.to(base)
     if cfg.d_arch == 'skip':
-        x = x + _conv_layer(P, 'b4.fromrgb.', img.to(torch.float32), act='lrelu')
+        x = x + _conv_layer(P, 'b4.fromrgb.', img.to(base), act='lrelu')
     if cfg.mbstd_num_channels > 0:
         x = _mbstd(x, cfg.mbstd_group_size, cfg.mbstd_num_channels)
     x = _conv_layer(P, 'b4.conv.', x, act='lrelu', clamp=cfg.conv_clamp)

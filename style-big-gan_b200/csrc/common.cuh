@@ -24,6 +24,7 @@ int num_sms();
     const int want_ = (int)(bytes);                                                                      \
     if (dev_ < 0 || dev_ >= 64 || done_[dev_].load(std::memory_order_acquire) < want_) {                 \
       cudaError_t e_ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, want_);   \
+      if (e_ != cudaSuccess) (void)cudaGetLastError();      /* do not leave the error for the next launch check */ \
       SGB_REQUIRE(e_ == cudaSuccess, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e_));    \
       if (dev_ >= 0 && dev_ < 64) done_[dev_].store(want_, std::memory_order_release);                   \
     }                                                                                                    \

@@ -13,6 +13,8 @@ int conv_forward_halo(const sgb_conv_desc* d, const void* x, const void* w, void
 int conv_wgrad_umma(const sgb_conv_desc* d, const void* x, const void* dy, void* dw, cudaStream_t s);
 bool conv_wgrad_halo_eligible(const sgb_conv_desc* d);
 int conv_wgrad_halo(const sgb_conv_desc* d, const void* x, const void* dy, void* dw, cudaStream_t s);
+bool conv_tma_eligible(const sgb_conv_desc* d);
+int conv_forward_tma(const sgb_conv_desc* d, const void* x, const void* w, void* y, cudaStream_t s);
 bool conv_small_eligible(const sgb_conv_desc* d);
 int conv_forward_small(const sgb_conv_desc* d, const void* x, const void* w, void* y, cudaStream_t s);
 
@@ -51,11 +53,13 @@ extern "C" int sgb_conv2d_wgrad_uses_tensor_cores(const sgb_conv_desc* d) {
   return (d && !d->transposed) ? wgrad_route(d) : 0;
 }
 
-// 1 = tcgen05 kernels, 2 = the small-co 1x1 bandwidth kernel (conv_small.cu), 0 = generic SIMT kernel
+// 1 = tcgen05 kernels (cp.async-staged patches), 3 = tcgen05 kernel with TMA-staged patches (conv_tma.cuh), 2 = the small-co
+// 1x1 bandwidth kernel (conv_small.cu), 0 = generic SIMT kernel
 extern "C" int sgb_conv2d_uses_tensor_cores(const sgb_conv_desc* d) {
   if (!d) return 0;
   if (conv_small_eligible(d)) return 2;
-  return conv_umma_eligible(d) ? 1 : 0;
+  if (!conv_umma_eligible(d)) return 0;
+  return (d->force_simt != 2 && conv_tma_eligible(d)) ? 3 : 1;
 }
 
 extern "C" int sgb_conv2d_forward(const sgb_conv_desc* d, const void* x, const void* w, void* y, void* stream) {
@@ -65,6 +69,7 @@ extern "C" int sgb_conv2d_forward(const sgb_conv_desc* d, const void* x, const v
   cudaStream_t s = (cudaStream_t)stream;
   if (conv_small_eligible(d)) return conv_forward_small(d, x, w, y, s);
   if (conv_umma_eligible(d)) {
+    if (d->force_simt != 2 && conv_tma_eligible(d)) return conv_forward_tma(d, x, w, y, s);
     if (d->force_simt != 2 && conv_halo_eligible(d)) return conv_forward_halo(d, x, w, y, s);
     return conv_forward_umma(d, x, w, y, s);
   }

@@ -1,0 +1,70 @@
+// Host side of the TMA-staged convolution kernel (conv_tma.cuh): eligibility, (BN, KB, GT) choice, the driver entry point
+// for tensor-map encoding, and the fp16 / fp32 instantiations.
+#include <cstdlib>
+#include "conv_tma.cuh"
+
+namespace sgb {
+
+PFN_encodeTiled tma_encode_fn() {
+  static PFN_encodeTiled fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return (PFN_encodeTiled)p;
+  }();
+  return fn;
+}
+
+// which convolutions take the TMA kernel: stride 1 (conv2d and conv_transpose2d), kernels up to 3x3, fp16 / fp32-as-TF32,
+// images of at least 32 rows (smaller ones: conv_halo_kernel's tiles straddle images, per-image tiles would be mostly padding),
+// a channel count whose bytes are a multiple of 16 (tensor-map strides), no fused epilogue.
+// SGB_TMA: 1 (default) = on, 0 = off (A/B)
+static bool tma_geometry_ok(const sgb_conv_desc* d) {
+  static const int on = [] { const char* e = getenv("SGB_TMA"); return e ? atoi(e) : 1; }();
+  if (!on) return false;
+  if (d->dtype != SGB_F16 && d->dtype != SGB_F32) return false;
+  if (d->stride != 1 || d->kh > 3 || d->kw > 3 || d->groups != 1) return false;
+  if (d->out_scale || d->noise || d->bias || d->act != 0) return false;
+  static const int force_g = [] { const char* e = getenv("SGB_TMA_FORCE"); return e ? atoi(e) : 0; }();
+  if ((d->out_h < 32 || d->out_w < 32) && !force_g) return false;
+  if (!d->transposed) { if (d->out_h != d->in_h + 2 * d->pad_y - d->kh + 1 || d->out_w != d->in_w + 2 * d->pad_x - d->kw + 1) return false; }
+  else { if (d->out_h != d->in_h - 2 * d->pad_y + d->kh - 1 || d->out_w != d->in_w - 2 * d->pad_x + d->kw - 1) return false;
+         if (d->pad_y > d->kh - 1 || d->pad_x > d->kw - 1) return false; }
+  const int es = d->dtype == SGB_F16 ? 2 : 4;
+  if ((d->ci * es) % 16 != 0) return false;
+  // tensor-map limits: strides < 2^40 bytes, multiples of 16 bytes; dims < 2^32
+  for (int i : {0, 2, 3}) if ((d->x_strides[i] * es) % 16 != 0 || d->x_strides[i] * es >= ((int64_t)1 << 40)) return false;
+  if (d->x_strides[1] != 1 || d->y_strides[1] != 1) return false;
+  return true;
+}
+
+// (BN, KB, GT) for this descriptor, or false when the kernel has no instantiation for it
+static bool tma_pick(const sgb_conv_desc* d, int& bn, int& kb, int& gt) {
+  bn = conv_bn(d);
+  if (bn < 32) return false;
+  const int es = d->dtype == SGB_F16 ? 2 : 4;
+  // K block = one swizzle row per pixel: 64 bytes (SWIZZLE_64B) when that already holds all channels, else 128 bytes; the
+  // super-tile width keeps a patch stage near 40 KB either way (18 x 34 x 64 B, 18 x 18 x 128 B)
+  kb = (d->ci * es <= 64) ? 64 : 128;
+  gt = (kb == 64) ? 4 : 2;
+  if (kb == 64 && bn > 64) return false;
+  // enough tiles for every SM (SGB_TMA_FORCE=1: take small problems too -- tests)
+  static const int force = [] { const char* e = getenv("SGB_TMA_FORCE"); return e ? atoi(e) : 0; }();
+  const int64_t tiles = (int64_t)d->n * ((d->out_h + 15) / 16) * ((d->out_w + 8 * gt - 1) / (8 * gt)) * ((d->co + bn - 1) / bn);
+  if (tiles < num_sms() && !force) return false;
+  return true;
+}
+
+bool conv_tma_eligible(const sgb_conv_desc* d) {
+  int bn, kb, gt;
+  return tma_geometry_ok(d) && tma_pick(d, bn, kb, gt) && tma_encode_fn() != nullptr;
+}
+
+int conv_forward_tma(const sgb_conv_desc* d, const void* x, const void* w, void* y, cudaStream_t s) {
+  int bn, kb, gt;
+  SGB_REQUIRE(tma_geometry_ok(d) && tma_pick(d, bn, kb, gt), "geometry not supported by the TMA kernel");
+  if (d->dtype == SGB_F16) return dispatch_tma<__half, 0>(bn, kb, gt, d, x, w, y, s);
+  return dispatch_tma<float, 2>(bn, kb, gt, d, x, w, y, s);
+}
+
+}  // namespace sgb

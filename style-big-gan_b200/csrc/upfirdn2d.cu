@@ -15,6 +15,7 @@
 //                             few input pixels those 4 outputs share into registers once (7 / 4 / 10 vectors for
 //                             (1,1) / (2,1) / (1,2)) and applies the taps with compile-time indexing.  CTAs cover
 //                             compact 4-row tiles so the vertical reuse is served by L1.
+#include <cstdlib>
 #include <type_traits>
 #include "common.cuh"
 
@@ -239,9 +240,223 @@ __global__ void __launch_bounds__(256) upfirdn2d_cl_kernel(UpfirdnParams p, int 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// channels_last STRIP kernel (the default for channels_last tensors, filters up to 4x4, (up, down) in {(1,1),(2,1),(1,2)}).
+// A thread owns 16 bytes of channels x PX consecutive output columns and walks DOWN a strip of `rows` output rows.  Every
+// input row of the strip is loaded ONCE (NIX 128-bit loads, the next row prefetched while the current one is used) and
+// scattered into a ring of SLOTS row accumulators; an output row is stored as soon as its last input row has been added.
+// Compared with upfirdn2d_cl_kernel (a thread = 4 outputs of ONE row, 4 filter rows x NIX loads each, tiny CTAs) this cuts
+// the load instructions per output 4x and amortises CTA start-up over rows x PX outputs per thread.
+// The ring indices are compile-time: the input-row loop is unrolled by UNR and slot(k, ty) only depends on k mod UNR.
+// Rank-1 filters (setup_filter's outer product, e.g. [1,3,3,1] x [1,3,3,1]) are detected in the kernel and applied
+// separably: FT/UP horizontal + 1 vertical FMA per (input row, tap row) instead of FT/UP x taps (halves the FP32 work, which
+// is what bounds 16-bit tensors: two elements per 4 bytes of traffic, fp32 accumulation).
+//   PARX = padx0 & 1, PARY = pady0 & 1 (UP == 2 only: fix the polyphase pattern at compile time).
+template <class T, int UP, int DOWN, int PARX, int PARY>
+__global__ void __launch_bounds__(256) upfirdn2d_strip_kernel(UpfirdnParams p, int cv_total, int cvb, int xgs, int rows) {
+  constexpr int VEC = Vec16<T>::N;
+  constexpr int FT = 4;
+  constexpr int PX = (VEC == 4) ? 4 : 2;
+  constexpr int NIX = ((PX - 1) * DOWN + FT - 1) / UP + 1;
+  constexpr int SLOTS = (DOWN == 2) ? 2 : 4;
+  constexpr int UNR = (UP == 2) ? 2 : 4;
+  __shared__ float sf[FT * FT];
+  __shared__ float sfx[FT], sfy[FT];
+  __shared__ int s_sep;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  if (tid < FT * FT) {
+    const int ty = tid / FT, tx = tid % FT;
+    float v = 0.f;
+    if (ty < p.fh && tx < p.fw) {
+      const int fy = p.flip ? ty : p.fh - 1 - ty, fx = p.flip ? tx : p.fw - 1 - tx;
+      v = p.f[fy * p.f_sy + fx * p.f_sx] * p.gain;
+    }
+    sf[tid] = v;
+  }
+  __syncthreads();
+  if (tid == 0) {      // rank-1 test: f[ty][tx] == fy[ty] * fx[tx] with fx = the row of the largest tap
+    int best = 0;
+    for (int i = 1; i < FT * FT; i++) if (fabsf(sf[i]) > fabsf(sf[best])) best = i;
+    const int r0 = best / FT, c0 = best % FT;
+    const float piv = sf[best];
+    int sep = piv != 0.f;
+    float fx_[FT], fy_[FT];
+    for (int i = 0; i < FT; i++) { fx_[i] = sf[r0 * FT + i]; fy_[i] = sep ? sf[i * FT + c0] / piv : 0.f; }
+    for (int i = 0; i < FT * FT && sep; i++)
+      if (fabsf(sf[i] - fy_[i / FT] * fx_[i % FT]) > 1e-6f * fabsf(piv)) sep = 0;
+    for (int i = 0; i < FT; i++) { sfx[i] = fx_[i]; sfy[i] = fy_[i]; }
+    s_sep = sep;
+  }
+  __syncthreads();
+  const bool sep = s_sep != 0;
+
+  const int cchunks = (cv_total + cvb - 1) / cvb;
+  const int n = blockIdx.z / cchunks;
+  const int cv = (blockIdx.z - n * cchunks) * cvb + threadIdx.x;
+  const int oy0 = blockIdx.y * rows;
+  const int ox0 = (blockIdx.x * xgs + threadIdx.y) * PX;
+  if (cv >= cv_total || ox0 >= p.out_w) return;
+  const int c0 = cv * VEC;
+  const int R = min(rows, p.out_h - oy0);
+
+  const int base_y = oy0 * DOWN - p.pady0;
+  const int iy0 = (UP == 1) ? base_y : ((base_y + PARY) >> 1);          // UP == 2: base_y has parity PARY (oy0 is even)
+  const int K = (UP == 2) ? ((R + 2 - PARY) / 2 + 1) : ((DOWN == 2) ? 2 * R + 2 : R + 3);
+  const int bx = ox0 * DOWN - p.padx0;
+  const int ix_first = (UP == 1) ? bx : ((bx + PARX) >> 1);             // UP == 2: bx has parity PARX (ox0 is even)
+  const bool interior = ix_first >= 0 && ix_first + NIX <= p.in_w;
+  const T* xn = (const T*)p.x + (int64_t)n * p.xs[0] + c0;
+  T* yn = (T*)p.y + (int64_t)n * p.ys[0] + c0;
+
+  float fr[FT * FT], fxr[FT], fyr[FT];
+#pragma unroll
+  for (int i = 0; i < FT * FT; i++) fr[i] = sf[i];
+#pragma unroll
+  for (int i = 0; i < FT; i++) { fxr[i] = sfx[i]; fyr[i] = sfy[i]; }
+
+  float acc[SLOTS][PX][VEC];
+#pragma unroll
+  for (int s = 0; s < SLOTS; s++)
+#pragma unroll
+    for (int j = 0; j < PX; j++)
+#pragma unroll
+      for (int e = 0; e < VEC; e++) acc[s][j][e] = 0.f;
+
+  auto load_row = [&](int k, Vec16<T> (&in)[NIX]) -> bool {
+    const int iy = iy0 + k;
+    if (k >= K || iy < 0 || iy >= p.in_h) return false;
+    const T* xr = xn + (int64_t)iy * p.xs[2];
+    if (interior) {
+      const T* xc = xr + (int64_t)ix_first * p.xs[3];
+#pragma unroll
+      for (int i = 0; i < NIX; i++) in[i].raw = __ldg((const uint4*)(xc + (int64_t)i * p.xs[3]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < NIX; i++) {
+        const int ix = ix_first + i;
+        in[i].raw = (ix >= 0 && ix < p.in_w) ? __ldg((const uint4*)(xr + (int64_t)ix * p.xs[3])) : make_uint4(0, 0, 0, 0);
+      }
+    }
+    return true;
+  };
+  auto store_row = [&](int jc, float (&a)[PX][VEC]) {
+    if (jc >= 0 && jc < R) {
+      T* yp = yn + (int64_t)(oy0 + jc) * p.ys[2];
+#pragma unroll
+      for (int j = 0; j < PX; j++) {
+        if (ox0 + j < p.out_w) {
+          Vec16<T> o;
+#pragma unroll
+          for (int e = 0; e < VEC; e++) o.v[e] = from_acc<T>(a[j][e]);
+          *(uint4*)(yp + (int64_t)(ox0 + j) * p.ys[3]) = o.raw;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < PX; j++)
+#pragma unroll
+        for (int e = 0; e < VEC; e++) a[j][e] = 0.f;
+    }
+  };
+
+  Vec16<T> nxt[NIX];
+  bool nxt_ok = load_row(0, nxt);
+  for (int k0 = 0; k0 < K; k0 += UNR) {
+#pragma unroll
+    for (int kk = 0; kk < UNR; kk++) {
+      const int k = k0 + kk;
+      if (k < K) {
+        Vec16<T> cur[NIX];
+#pragma unroll
+        for (int i = 0; i < NIX; i++) cur[i].raw = nxt[i].raw;
+        const bool cur_ok = nxt_ok;
+        nxt_ok = load_row(k + 1, nxt);
+        if (cur_ok) {
+          float h[PX][VEC];
+          if (sep) {                  // horizontal pass once per input row
+#pragma unroll
+            for (int j = 0; j < PX; j++) {
+#pragma unroll
+              for (int e = 0; e < VEC; e++) h[j][e] = 0.f;
+#pragma unroll
+              for (int tx = 0; tx < FT; tx++) {
+                const int rel = j * DOWN + tx - ((UP == 2) ? PARX : 0);
+                if (UP == 2 && (rel & 1)) continue;
+                const int i = rel / UP;
+                if (rel < 0 || i >= NIX) continue;
+#pragma unroll
+                for (int e = 0; e < VEC; e++) h[j][e] += to_acc<T>(cur[i].v[e]) * fxr[tx];
+              }
+            }
+          }
+#pragma unroll
+          for (int ty = 0; ty < FT; ty++) {
+            // output row (relative to oy0) this (input row, tap row) pair feeds, and its ring slot (compile-time)
+            int jrel; int slot;
+            if (UP == 1 && DOWN == 1) { jrel = k - ty; slot = (kk - ty) & 3; }
+            else if (DOWN == 2) { if ((kk - ty) & 1) continue; jrel = (k - ty) >> 1; slot = ((kk - ty + 8) >> 1) & 1; }
+            else { jrel = 2 * k + PARY - ty; slot = (2 * kk + PARY - ty) & 3; }
+            if (jrel < 0 || jrel >= R) continue;
+            if (sep) {
+              const float fv = fyr[ty];
+#pragma unroll
+              for (int j = 0; j < PX; j++)
+#pragma unroll
+                for (int e = 0; e < VEC; e++) acc[slot][j][e] += h[j][e] * fv;
+            } else {
+#pragma unroll
+              for (int j = 0; j < PX; j++) {
+#pragma unroll
+                for (int tx = 0; tx < FT; tx++) {
+                  const int rel = j * DOWN + tx - ((UP == 2) ? PARX : 0);
+                  if (UP == 2 && (rel & 1)) continue;
+                  const int i = rel / UP;
+                  if (rel < 0 || i >= NIX) continue;
+                  const float fv = fr[ty * FT + tx];
+#pragma unroll
+                  for (int e = 0; e < VEC; e++) acc[slot][j][e] += to_acc<T>(cur[i].v[e]) * fv;
+                }
+              }
+            }
+          }
+        }
+        // output rows whose last input row was k
+        if (UP == 1 && DOWN == 1) store_row(k - 3, acc[(kk - 3) & 3]);
+        else if (DOWN == 2) { if (kk & 1) store_row((k - 3) >> 1, acc[((kk - 3 + 8) >> 1) & 1]); }
+        else { store_row(2 * k + PARY - 3, acc[(2 * kk + PARY - 3) & 3]); store_row(2 * k + PARY - 2, acc[(2 * kk + PARY - 2) & 3]); }
+      }
+    }
+  }
+}
+
 }  // namespace sgb
 
 using namespace sgb;
+
+template <class T>
+static int launch_strip(const UpfirdnParams& p, cudaStream_t s) {
+  constexpr int VEC = Vec16<T>::N;
+  constexpr int PX = (VEC == 4) ? 4 : 2;
+  const int cv_total = p.c / VEC;
+  int cvb = 1; while (cvb < cv_total && cvb < 32) cvb <<= 1;
+  const int xgs = 256 / cvb;                            // x groups (of PX outputs) per CTA
+  const int64_t gx = ceil_div(p.out_w, xgs * PX), gzz = (int64_t)p.n * ceil_div(cv_total, cvb);
+  int rows = p.out_h >= 128 ? 32 : (p.out_h >= 32 ? 16 : 8);
+  while (rows > 8 && gx * ceil_div(p.out_h, rows) * gzz < 2 * (int64_t)num_sms()) rows >>= 1;
+  const int64_t gy = ceil_div(p.out_h, rows);
+  if (gy > 65535 || gzz > 65535) return 1;
+  dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)gzz), block(cvb, xgs);
+  const int px = p.padx0 & 1, py = p.pady0 & 1;
+  if (p.upx == 1 && p.downx == 1)           upfirdn2d_strip_kernel<T, 1, 1, 0, 0><<<grid, block, 0, s>>>(p, cv_total, cvb, xgs, rows);
+  else if (p.downx == 2)                    upfirdn2d_strip_kernel<T, 1, 2, 0, 0><<<grid, block, 0, s>>>(p, cv_total, cvb, xgs, rows);
+  else if (px == 0 && py == 0)              upfirdn2d_strip_kernel<T, 2, 1, 0, 0><<<grid, block, 0, s>>>(p, cv_total, cvb, xgs, rows);
+  else if (px == 1 && py == 1)              upfirdn2d_strip_kernel<T, 2, 1, 1, 1><<<grid, block, 0, s>>>(p, cv_total, cvb, xgs, rows);
+  else if (px == 0)                         upfirdn2d_strip_kernel<T, 2, 1, 0, 1><<<grid, block, 0, s>>>(p, cv_total, cvb, xgs, rows);
+  else                                      upfirdn2d_strip_kernel<T, 2, 1, 1, 0><<<grid, block, 0, s>>>(p, cv_total, cvb, xgs, rows);
+  SGB_LAUNCH_CHECK();
+  return 0;
+}
+template <> int launch_strip<double>(const UpfirdnParams&, cudaStream_t) { return 1; }
 
 template <class T>
 static int launch_upfirdn(const UpfirdnParams& p, cudaStream_t s) {
@@ -266,6 +481,12 @@ static int launch_upfirdn(const UpfirdnParams& p, cudaStream_t s) {
   const bool cl_ok = sq && small && p.xs[1] == 1 && p.ys[1] == 1 && p.c % VEC == 0 && aligned16(p.x) && aligned16(p.y) &&
                      p.xs[0] % VEC == 0 && p.xs[2] % VEC == 0 && p.xs[3] % VEC == 0 &&
                      p.ys[0] % VEC == 0 && p.ys[2] % VEC == 0 && p.ys[3] % VEC == 0 && !std::is_same<T, double>::value;
+  // the strip kernel is opt-in (SGB_FIR_STRIP=1): measured on a B200 it does not beat upfirdn2d_cl_kernel (profiles/README.md:
+  // 0.223 vs 0.248 ms on fp16 [4,32,1025,1025] but 0.292 vs 0.277 ms on fp32 [32,64,257,257], slower for up / down 2)
+  static const int fir_strip = [] { const char* e = getenv("SGB_FIR_STRIP"); return e ? atoi(e) : 0; }();
+  if (cl_ok && fir_strip) {
+    if (int r = launch_strip<T>(p, s)) { if (r < 0) return 1; } else return 0;      // > 0: not taken, fall through
+  }
   if (cl_ok) {
     const int cv_total = p.c / VEC;
     int cvb = 1; while (cvb < cv_total && cvb < 32) cvb <<= 1;

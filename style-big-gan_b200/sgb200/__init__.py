@@ -14,5 +14,7 @@ __version__ = '0.1.0'
 
 
 def install(*a, **k):
-    from .install import install as _install
-    return _install(*a, **k)
+    # the implementation lives in `_install.py`: a submodule named `install` would replace this function as the package
+    # attribute `sgb200.install` the first time it is imported, and the second `sgb200.install()` would fail
+    from ._install import install as _impl
+    return _impl(*a, **k)

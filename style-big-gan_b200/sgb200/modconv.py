@@ -60,14 +60,14 @@ def modulated_conv2d(
     if not fused_modconv:
         x = _cr.conv2d_resample(x=x, w=weight.to(x.dtype), f=resample_filter, up=up, down=down, padding=padding,
                                 flip_weight=flip_weight, in_scale=styles)
-        if noise is not None:
-            noise = noise.to(x.dtype)
-            if noise.ndim < 4 or noise.shape[0] != batch_size:
-                noise = noise.expand(batch_size, 1, x.shape[2], x.shape[3])
+        if noise is not None and (noise.ndim < 4 or noise.shape[0] != batch_size):
+            noise = noise.expand(batch_size, 1, x.shape[2], x.shape[3])
         if demodulate:
+            # the noise stays in its own (fp32) type: the kernel adds it in the accumulator type, and its gradient (the channel
+            # sum of dy) is returned in fp32 instead of being rounded to fp16 first as `noise.to(x.dtype)` would make it
             return _fma.scale_nc(x, dcoefs, noise)
         if noise is not None:
-            return x.add_(noise)
+            return x.add_(noise.to(x.dtype))
         return x
 
     # grouped convolution with one group per sample (reference :91-99); used in eval / G_ema mode

@@ -233,8 +233,8 @@ def _conv2d_op(transpose, weight_shape, stride, padding, output_padding, dilatio
                 ws = _attach_workspace(d, input.device)
                 tc = _lib.lib().sgb_conv2d_uses_tensor_cores(d)
                 tag = (f"{str(input.dtype)[6:]} x[{input.shape[0]},{ci},{input.shape[2]},{input.shape[3]}] co{co} k{kh} s{s}"
-                       f"{' T' if transpose else ''}{' mod' if sc is not None else ''}") if _lib.PROFILE is not None else None
-                with torch.cuda.device(input.device), _lib.prof(('conv_fwd_simt', 'conv_fwd_tc', 'conv_fwd_small')[tc], flops, nbytes, tag):
+                       f"{' T' if transpose else ''}{' mod' if sc is not None else ''}{' tma' if tc == 3 else ''}") if _lib.PROFILE is not None else None
+                with torch.cuda.device(input.device), _lib.prof(('conv_fwd_simt', 'conv_fwd_tc', 'conv_fwd_small', 'conv_fwd_tc')[tc], flops, nbytes, tag):
                     rc = _lib.lib().sgb_conv2d_forward(d, _lib.ptr(x_), _lib.ptr(w), _lib.ptr(y), _lib.stream_ptr(input.device))
                 _lib.check(rc, 'conv2d_forward')
             ctx.save_for_backward(input, weight, in_scale)

