@@ -285,6 +285,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(HaloParams p
       const uint32_t b_stage_u = (uint32_t)(p.tps * B_TAP_BYTES) >> 4;
       int sa = 0, sb = 0, li = 0;
       uint32_t pha = 0, phb = 0;
+      const uint32_t leader = elect_one();
       for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, li++) {
         const int buf = (NBUF == 2) ? (li & 1) : 0;
         const uint32_t eph = (NBUF == 2) ? ((li >> 1) & 1) : (li & 1);
@@ -300,34 +301,31 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(HaloParams p
             mbar_wait(smem_u32(&b_full[sb]), phb);
             tc_fence_after();
             const uint32_t b_lo0 = b_lo_base + sb * b_stage_u;
-            if (lane == 0) {
-              for (int t = 0; t < p.tps; t++) {
-                const int tap = tap0 + t;
-                const int acc = (MODE == 2) ? p.tap_acc[tap] : 0;
-                const uint32_t a_lo = a_lo0 + (uint32_t)p.tap_aoff[tap];
-                const uint32_t b_lo = b_lo0 + t * (B_TAP_BYTES >> 4);
-                const uint32_t first = (started >> acc) & 1u;
+            // warp-uniform issue (umma.cuh: elect_one / umma_lh_pred): every lane runs the loop so that the descriptor
+            // arithmetic stays in uniform registers; the elected lane issues
+            for (int t = 0; t < p.tps; t++) {
+              const int tap = tap0 + t;
+              const int acc = (MODE == 2) ? p.tap_acc[tap] : 0;
+              const uint32_t a_lo = a_lo0 + (uint32_t)p.tap_aoff[tap];
+              const uint32_t b_lo = b_lo0 + t * (B_TAP_BYTES >> 4);
+              const uint32_t first = (started >> acc) & 1u;
 #pragma unroll
-                for (int g = 0; g < GT; g++) {
-                  if (p.debug & 4) break;
+              for (int g = 0; g < GT; g++) {
+                if (p.debug & 4) break;
 #pragma unroll
-                  for (int kk = 0; kk < CH / 2; kk++)
-                    umma_lh<KIND>(tmem_d + (g * NPH + acc) * BN, a_lo + g * TILE_W + kk * kk_u, a_hi, b_lo + kk * (2 * BN), b_hi, IDESC,
-                                  first | (uint32_t)kk);
-                }
-                started |= 1u << acc;
+                for (int kk = 0; kk < CH / 2; kk++)
+                  umma_lh_pred<KIND>(leader, tmem_d + (g * NPH + acc) * BN, a_lo + g * TILE_W + kk * kk_u, a_hi, b_lo + kk * (2 * BN), b_hi, IDESC,
+                                     first | (uint32_t)kk);
               }
-              umma_commit(smem_u32(&b_empty[sb]));
+              started |= 1u << acc;
             }
-            __syncwarp();
+            umma_commit_pred(leader, smem_u32(&b_empty[sb]));
             if (++sb == SB) { sb = 0; phb ^= 1; }
           }
-          if (lane == 0) umma_commit(smem_u32(&a_empty[sa]));
-          __syncwarp();
+          umma_commit_pred(leader, smem_u32(&a_empty[sa]));
           if (++sa == SA) { sa = 0; pha ^= 1; }
         }
-        if (lane == 0) umma_commit(smem_u32(&acc_full[buf]));
-        __syncwarp();
+        umma_commit_pred(leader, smem_u32(&acc_full[buf]));
       }
     }
   } else if (warp == 5) {

@@ -13,7 +13,9 @@
 // That is the canonical K-major swizzled UMMA operand: a core-matrix group = 8 consecutive pixels of one patch row,
 // SBO = one patch row (HC * KB bytes) = the next row of the 16 x 8 output tile.  The halo trick of conv_halo_kernel
 // carries over: a filter tap (ky, kx) and the tile index g within the super-tile only move the descriptor's start address
-// by whole pixels; the swizzle phase of a shifted start goes into the descriptor's base-offset field.
+// by whole pixels.  Established by experiment on a B200 (benchmarks/experiments/tma_check.py, SGB_TMA_BO=0|1): the UMMA
+// swizzle is a function of the ABSOLUTE shared-memory address, so a start address shifted by whole rows needs base_offset = 0;
+// putting the start's swizzle phase into the descriptor's base-offset field gives wrong results for every shifted tap.
 //
 // Weights: the pre-packed no-swizzle B tiles of conv_umma.cu (pack_weights_umma), streamed with cp.async.bulk as before.
 // Tiles are per image (a super-tile = 16 x 8*GT output pixels of one image), so one box covers a patch.
@@ -47,7 +49,10 @@ struct TmaConvParams {
   int stg_off;
   int vec_store;
   int pass;                 // 1: the operand pass runs (in_scale and / or TF32 rounding)
-  int bo_mode;              // descriptor base offset: 1 = swizzle phase of the start address, 0 = always zero (experiment)
+  int wres;                 // 1: the whole packed weight tensor is loaded into shared memory once and stays resident
+  int w_bytes;              //    its size
+  int bo_mode;              // descriptor base offset: 0 = always zero (correct), 1 = swizzle phase of the start address (the
+                            // experiment that showed it is wrong; kept for benchmarks/experiments/tma_check.py)
   int tap_aoff[9];          // per tap: patch offset in pixels
 };
 
@@ -88,6 +93,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_c
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ uint64_t a_full[TMA_MAX_SA], a_ready[TMA_MAX_SA], a_empty[TMA_MAX_SA], b_full[TMA_MAX_SB], b_empty[TMA_MAX_SB], acc_full[2], acc_empty[2];
+  __shared__ uint64_t w_full;
   __shared__ uint32_t tmem_base_slot;
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);      // swizzled stages: 1024-byte aligned
 
@@ -104,6 +110,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_c
       }
       for (int s = 0; s < TMA_MAX_SB; s++) { mbar_init(smem_u32(&b_full[s]), 1); mbar_init(smem_u32(&b_empty[s]), 1); }
       for (int s = 0; s < 2; s++) { mbar_init(smem_u32(&acc_full[s]), 1); mbar_init(smem_u32(&acc_empty[s]), 4); }
+      mbar_init(smem_u32(&w_full), 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -191,49 +198,71 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_c
     const uint32_t a_base_addr = smem_u32(a_base);
     int sa = 0, sb = 0, li = 0;
     uint32_t pha = 0, phb = 0;
+    constexpr int HALVES_M = 8 / CH;
+    const int cb128_m = (p.cblocks + HALVES_M - 1) / HALVES_M;
+    const uint32_t leader = elect_one();            // the whole warp runs the loop; this lane issues
+    if (p.wres) { mbar_wait(smem_u32(&w_full), 0); tc_fence_after(); }
     for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, li++) {
       const int buf = (NBUF == 2) ? (li & 1) : 0;
       const uint32_t eph = (NBUF == 2) ? ((li >> 1) & 1) : (li & 1);
       mbar_wait(smem_u32(&acc_empty[buf]), eph ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + buf * (NACC * BN);
+      const int ntile_m = (int)(tile % p.ntiles);
       for (int cb = 0; cb < p.cblocks; cb++) {
         mbar_wait(smem_u32(p.pass ? &a_ready[sa] : &a_full[sa]), pha);
         tc_fence_after();
         const uint32_t a_stage = a_base_addr + sa * (uint32_t)p.a_stage_bytes;
+        if (p.wres) {
+          // resident weights: tile (ntile, tap, cb) sits where the packed image has it
+          for (int tap = 0; tap < p.taps; tap++) {
+            const uint32_t woff = (uint32_t)(((ntile_m * p.taps + tap) * cb128_m + cb / HALVES_M) * (BN * 128) + (cb % HALVES_M) * B_TAP_BYTES);
+            const uint32_t b_lo = b_lo_base + (woff >> 4);
+#pragma unroll
+            for (int g = 0; g < GT; g++) {
+              const uint32_t start = a_stage + (uint32_t)(p.tap_aoff[tap] + g * TMA_TILE_W) * KB;
+              const uint32_t a_lo = ((start >> 4) & 0x3FFF) | (1u << 16);
+#pragma unroll
+              for (int kk = 0; kk < KSTEPS; kk++)
+                umma_lh_pred<KIND>(leader, tmem_d + g * BN, a_lo + kk * 2, a_hi0, b_lo + kk * (2 * BN), b_hi, IDESC, (uint32_t)((cb | tap | kk) != 0));
+            }
+          }
+        } else
         for (int tap0 = 0; tap0 < p.taps; tap0 += p.tps) {
           mbar_wait(smem_u32(&b_full[sb]), phb);
           tc_fence_after();
           const uint32_t b_lo0 = b_lo_base + sb * b_stage_u;
-          if (lane == 0) {
-            for (int t = 0; t < p.tps; t++) {
-              const int tap = tap0 + t;
-              const uint32_t b_lo = b_lo0 + t * (B_TAP_BYTES >> 4);
+          for (int t = 0; t < p.tps; t++) {
+            const int tap = tap0 + t;
+            const uint32_t b_lo = b_lo0 + t * (B_TAP_BYTES >> 4);
 #pragma unroll
-              for (int g = 0; g < GT; g++) {
-                const uint32_t start = a_stage + (uint32_t)(p.tap_aoff[tap] + g * TMA_TILE_W) * KB;
-                const uint32_t a_hi = a_hi0 | (p.bo_mode ? (((start >> 7) & 7u) << 17) : 0u);
-                const uint32_t a_lo = ((start >> 4) & 0x3FFF) | (1u << 16);
+            for (int g = 0; g < GT; g++) {
+              const uint32_t start = a_stage + (uint32_t)(p.tap_aoff[tap] + g * TMA_TILE_W) * KB;
+              const uint32_t a_hi = a_hi0 | (p.bo_mode ? (((start >> 7) & 7u) << 17) : 0u);
+              const uint32_t a_lo = ((start >> 4) & 0x3FFF) | (1u << 16);
 #pragma unroll
-                for (int kk = 0; kk < KSTEPS; kk++)
-                  umma_lh<KIND>(tmem_d + g * BN, a_lo + kk * 2, a_hi, b_lo + kk * (2 * BN), b_hi, IDESC, (uint32_t)((cb | tap | kk) != 0));
-              }
+              for (int kk = 0; kk < KSTEPS; kk++)
+                umma_lh_pred<KIND>(leader, tmem_d + g * BN, a_lo + kk * 2, a_hi, b_lo + kk * (2 * BN), b_hi, IDESC, (uint32_t)((cb | tap | kk) != 0));
             }
-            umma_commit(smem_u32(&b_empty[sb]));
           }
-          __syncwarp();
+          umma_commit_pred(leader, smem_u32(&b_empty[sb]));
           if (++sb == SB) { sb = 0; phb ^= 1; }
         }
-        if (lane == 0) umma_commit(smem_u32(&a_empty[sa]));
-        __syncwarp();
+        umma_commit_pred(leader, smem_u32(&a_empty[sa]));
         if (++sa == SA) { sa = 0; pha ^= 1; }
       }
-      if (lane == 0) umma_commit(smem_u32(&acc_full[buf]));
-      __syncwarp();
+      umma_commit_pred(leader, smem_u32(&acc_full[buf]));
     }
   } else if (warp == 5) {
     // =========================== weight loader ===========================
-    if (lane == 0) {
+    if (lane == 0 && p.wres) {
+      const uint32_t bar = smem_u32(&w_full);
+      mbar_arrive_expect_tx(bar, (uint32_t)p.w_bytes);
+      for (int off = 0; off < p.w_bytes; off += 16384) {
+        const int nb = (p.w_bytes - off < 16384) ? p.w_bytes - off : 16384;
+        bulk_copy_g2s(smem_u32(b_base) + off, (const uint8_t*)p.wpack + off, (uint32_t)nb, bar);
+      }
+    } else if (lane == 0) {
       int sb = 0;
       uint32_t phb = 0;
       // packed image: [ntile][tap][128-byte channel block][chunk (8)][row (BN)][16 B]; a stage takes CH chunks of it
@@ -375,7 +404,7 @@ int launch_tma(const sgb_conv_desc* d, const void* x, const void* w, void* y, cu
   const bool y_al = aligned16(y) && d->y_strides[0] % TC == 0 && d->y_strides[2] % TC == 0 && d->y_strides[3] % TC == 0;
   p.vec_store = (d->co % TC == 0 && y_al) ? 1 : 0;
   static const int no_round = [] { const char* e = getenv("SGB_TMA_NOROUND"); return e ? atoi(e) : 0; }();
-  static const int bo_mode = [] { const char* e = getenv("SGB_TMA_BO"); return e ? atoi(e) : 1; }();
+  static const int bo_mode = [] { const char* e = getenv("SGB_TMA_BO"); return e ? atoi(e) : 0; }();
   p.pass = (d->in_scale != nullptr || (KIND == 2 && !no_round)) ? 1 : 0;
   p.bo_mode = bo_mode;
   SGB_REQUIRE(aligned16(x) && aligned16(d->workspace), "x and workspace must be 16-byte aligned");
@@ -399,6 +428,21 @@ int launch_tma(const sgb_conv_desc* d, const void* x, const void* w, void* y, cu
   const int stg_bytes = 4 * 32 * PITCH;
   const int b_tap = BN * KB;
   int sa = 0, sb = 0, tps = 1;
+  // few channels: the whole packed weight tensor stays in shared memory (no weight stream, no b_full / b_empty hand-shakes)
+  {
+    const int cb128 = (p.cblocks * KB + 127) / 128;
+    const int64_t wb = (int64_t)p.ntiles * p.taps * cb128 * (BN * 128);
+    static const int no_res = [] { const char* e = getenv("SGB_TMA_NORES"); return e ? atoi(e) : 0; }();
+    p.wres = (!no_res && wb <= 80 * 1024) ? 1 : 0;
+    p.w_bytes = (int)wb;
+  }
+  if (p.wres) {
+    sa = (budget - stg_bytes - p.w_bytes) / p.a_stage_bytes;
+    if (sa > TMA_MAX_SA) sa = TMA_MAX_SA;
+    SGB_REQUIRE(sa >= 2, "shared memory budget exceeded");
+    p.sa = sa; p.sb = 2; p.tps = 1;
+    p.stg_off = sa * p.a_stage_bytes + (p.w_bytes + 1023) / 1024 * 1024;
+  } else {
   for (int cand = p.taps; cand >= 1; cand--) {
     if (p.taps % cand) continue;
     const int b_stage_c = cand * b_tap;
@@ -416,6 +460,7 @@ int launch_tma(const sgb_conv_desc* d, const void* x, const void* w, void* y, cu
   }
   p.sa = sa; p.sb = sb; p.tps = tps;
   p.stg_off = sa * p.a_stage_bytes + sb * b_stage;
+  }
   const size_t smem = (size_t)p.stg_off + stg_bytes + 2048;
   auto kern = conv_tma_kernel<T, KIND, BN, KB, GT>;
   SGB_REQUIRE(smem <= 226 * 1024, "shared memory plan exceeds 226 KB");

@@ -248,6 +248,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_halo_kernel(WgradHal
     // whole warp runs the loop (uniform values), lane 0 issues; descriptors as (lo, hi) halves, ring counters
     {
       const int mmas = p.TH * 8 / KPM;
+      const uint32_t leader = elect_one();
       const uint32_t a_hi = smem_desc_hi((uint32_t)p.a_plane), b_hi = smem_desc_hi((uint32_t)p.b_plane);
       const uint32_t a_lo_base = smem_desc_lo(smem_u32(smem), 128);
       const uint32_t b_lo_base = smem_desc_lo(smem_u32(smem) + (uint32_t)p.a_bytes, (uint32_t)(p.HC * 16));   // LBO: next tile row = next patch row
@@ -259,20 +260,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_halo_kernel(WgradHal
         mbar_wait(smem_u32(&full_bar[sa]), pha);
         tc_fence_after();
         const uint32_t a_lo0 = a_lo_base + sa * stage_u, b_lo0 = b_lo_base + sa * stage_u;
-        if (lane == 0) {
-          for (int kx = 0; kx < d.kw; kx++) {
-            const uint32_t b_lo = b_lo0 + (uint32_t)((kx % s) * p.QP + kx / s);
-            const uint32_t tm = tmem_base + kx * BNC;
+        for (int kx = 0; kx < d.kw; kx++) {          // warp-uniform issue (umma.cuh: elect_one / umma_lh_pred)
+          const uint32_t b_lo = b_lo0 + (uint32_t)((kx % s) * p.QP + kx / s);
+          const uint32_t tm = tmem_base + kx * BNC;
 #pragma unroll 4
-            for (int kk = 0; kk < mmas; kk++)
-              umma_lh<KIND>(tm, a_lo0 + kk * KPM, a_hi, b_lo + kk * b_row_u, b_hi, IDESC, (i > 0 || kk > 0) ? 1u : 0u);
-          }
-          umma_commit(smem_u32(&empty_bar[sa]));
+          for (int kk = 0; kk < mmas; kk++)
+            umma_lh_pred<KIND>(leader, tm, a_lo0 + kk * KPM, a_hi, b_lo + kk * b_row_u, b_hi, IDESC, (i > 0 || kk > 0) ? 1u : 0u);
         }
-        __syncwarp();
+        umma_commit_pred(leader, smem_u32(&empty_bar[sa]));
         if (++sa == SA) { sa = 0; pha ^= 1; }
       }
-      if (ntiles > 0 && lane == 0) umma_commit(smem_u32(&accum_bar));
+      if (ntiles > 0) umma_commit_pred(leader, smem_u32(&accum_bar));
     }
     __syncwarp();
   }

@@ -237,6 +237,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) conv_wgrad_tf32_kernel(WgradTf3
     // =========================== MMA issuer ===========================
     // whole warp runs the loop (uniform values), lane 0 issues; descriptors as (lo, hi) halves, ring counters
     {
+      const uint32_t leader = elect_one();
       const uint32_t IDESC = idesc_of(p.m64 ? 64u : 128u, (uint32_t)BNC);
       const uint32_t hi = smem_desc_hi(512) | (1u << 29);                     // SBO = 4 rows; layout type 1 (bits 61-63)
       const uint32_t a_lo_base = smem_desc_lo(smem_u32(smem), (uint32_t)p.a_blk);
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) conv_wgrad_tf32_kernel(WgradTf3
         mbar_wait(smem_u32(&full_bar[sa]), pha);
         tc_fence_after();
         const uint32_t a_lo0 = a_lo_base + sa * stage_u, b_lo0 = b_lo_base + sa * stage_u;
-        if (lane == 0 && p.stack) {
+        if (p.stack) {                                // warp-uniform issue (umma.cuh: elect_one / umma_lh_pred)
           // stride 1, three taps: tap kx of a 32-channel block is the same block one patch row further down, i.e. the
           // next N block of a descriptor whose LBO is one row (128 B).  One N = 96 MMA per block and tile row reads
           // the dy tile once for the three taps instead of three times.
@@ -260,23 +261,22 @@ __global__ void __launch_bounds__(WT_THREADS, 1) conv_wgrad_tf32_kernel(WgradTf3
             const uint32_t tm = tmem_base + cbk * 96;
 #pragma unroll 4
             for (int ty = 0; ty < p.TH; ty++)
-              umma_lh<2>(tm, a_lo0 + ty * 64, hi, b_lo + ty * b_row_u, hi, IDESC96, (i > 0 || ty > 0) ? 1u : 0u);
+              umma_lh_pred<2>(leader, tm, a_lo0 + ty * 64, hi, b_lo + ty * b_row_u, hi, IDESC96, (i > 0 || ty > 0) ? 1u : 0u);
           }
-          umma_commit(smem_u32(&empty_bar[sa]));
-        } else if (lane == 0) {
+          umma_commit_pred(leader, smem_u32(&empty_bar[sa]));
+        } else {
           for (int kx = 0; kx < d.kw; kx++) {
             const uint32_t b_lo = b_lo0 + (uint32_t)(((kx % s) * p.QP + kx / s) * 8);
             const uint32_t tm = tmem_base + kx * BNC;
 #pragma unroll 4
             for (int ty = 0; ty < p.TH; ty++)
-              umma_lh<2>(tm, a_lo0 + ty * 64, hi, b_lo + ty * b_row_u, hi, IDESC, (i > 0 || ty > 0) ? 1u : 0u);
+              umma_lh_pred<2>(leader, tm, a_lo0 + ty * 64, hi, b_lo + ty * b_row_u, hi, IDESC, (i > 0 || ty > 0) ? 1u : 0u);
           }
-          umma_commit(smem_u32(&empty_bar[sa]));
+          umma_commit_pred(leader, smem_u32(&empty_bar[sa]));
         }
-        __syncwarp();
         if (++sa == SA) { sa = 0; pha ^= 1; }
       }
-      if (ntiles > 0 && lane == 0) umma_commit(smem_u32(&accum_bar));
+      if (ntiles > 0) umma_commit_pred(leader, smem_u32(&accum_bar));
     }
     __syncwarp();
   }

@@ -166,7 +166,8 @@ def test_cuda_graph_phases_match_golden_and_eager(gold, mode):
             scale = max(float(ge.abs().max()), 1e-20)
             # same kernels, same inputs; the weight-gradient kernels reduce with atomics, so the sums differ in the last bits
             # (more visibly in the second-order phases, whose operands are themselves such sums)
-            assert float((ge - gg).abs().max()) <= 1e-3 * scale + 1e-12, f"{ph['name']}: graph replay differs from eager launch"
+            rtol = 1e-4 if mode == 'strict' else 5e-3
+            assert float((ge - gg).abs().max()) <= rtol * scale + 1e-12, f"{ph['name']}: graph replay differs from eager launch"
 
 
 @pytest.mark.gpu
