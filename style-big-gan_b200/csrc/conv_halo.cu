@@ -32,9 +32,21 @@ bool conv_halo_eligible(const sgb_conv_desc* d) { return conv_halo_mode(d) >= 0;
 
 // output-channel tile of the tensor-core kernels for this descriptor (also fixes the packed-weight layout)
 int conv_bn(const sgb_conv_desc* d) {
-  const int bn = pick_bn(d->co);
+  int bn = pick_bn(d->co);
   static const int m2bn = [] { const char* e = getenv("SGB_HALO_M2BN"); return e ? atoi(e) : 128; }();
-  if (d->force_simt != 2 && conv_halo_mode(d) == 2 && bn > m2bn) return m2bn;   // 4 accumulators must fit 512 TMEM columns
+  const int mode = (d->force_simt != 2) ? conv_halo_mode(d) : -1;
+  if (mode == 2 && bn > m2bn) bn = m2bn;   // 4 accumulators must fit 512 TMEM columns
+  // small images at small batch (the 4x4 ... 32x32 layers of a 4-image batch): a 256-channel output tile leaves a handful of
+  // CTAs, each streaming megabytes of weights through one SM (measured: [4,512,9,9] stride 2 at 0.11 ms = 85 GB/s of weight
+  // traffic).  Narrower output tiles spread the weight stream over more SMs; the patch re-reads this costs are tiny here.
+  static const int par_bn = [] { const char* e = getenv("SGB_HALO_PARBN"); return e ? atoi(e) : 1; }();
+  if (mode >= 0 && par_bn) {
+    int64_t tiles;
+    if (mode == 0) tiles = ceil_div((int64_t)d->n * (d->out_h + d->kh - 1), 16) * ceil_div(d->out_w, 8);
+    else if (mode == 1) tiles = (int64_t)d->n * ceil_div(d->out_h, 16) * ceil_div(d->out_w, 8);
+    else tiles = ceil_div((int64_t)d->n * (((d->out_h - 1 + d->pad_y) >> 1) + 2), 16) * ceil_div(((d->out_w - 1 + d->pad_x) >> 1) + 1, 8);
+    while (bn > 32 && tiles * ceil_div(d->co, bn) < num_sms()) bn >>= 1;
+  }
   return bn;
 }
 

@@ -41,7 +41,9 @@ static bool tma_geometry_ok(const sgb_conv_desc* d) {
 // (BN, KB, GT) for this descriptor, or false when the kernel has no instantiation for it
 static bool tma_pick(const sgb_conv_desc* d, int& bn, int& kb, int& gt) {
   bn = conv_bn(d);
-  if (bn < 32) return false;
+  // measured (benchmarks/experiments/tma_check.py): ahead of conv_halo_kernel up to 128 output channels, behind it at 256
+  // (GT = 2 against the halo kernel's wider super-tiles: the L2 weight stream per MMA doubles)
+  if (bn < 32 || bn > 128) return false;
   const int es = d->dtype == SGB_F16 ? 2 : 4;
   // K block = one swizzle row per pixel: 64 bytes (SWIZZLE_64B) when that already holds all channels, else 128 bytes; the
   // super-tile width keeps a patch stage near 40 KB either way (18 x 34 x 64 B, 18 x 18 x 128 B)

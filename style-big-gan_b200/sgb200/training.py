@@ -57,6 +57,7 @@ class TrainConfig:
     channels_last: bool = True
     noise_mode: str = 'random'
     seed: int = 0
+    force_flat_grads: bool = False    # tests: use the flat gradient buffers (the N > 1 path) on a single GPU
     allreduce_in_graph: bool = True   # N > 1 with cuda_graphs: capture the NCCL gradient all-reduce inside each phase graph
     cuda_graphs: bool = False      # capture each training phase in a CUDA graph and replay it (static shapes; removes the
                                    # per-launch host cost of ~3000 kernel launches per iteration)
@@ -225,9 +226,12 @@ class Trainer:
                                        capturable=cfg.cuda_graphs)
                 self.phases.append(dict(name=name + 'main', module=module, opt=opt, interval=1))
                 self.phases.append(dict(name=name + 'reg', module=module, opt=opt, interval=interval))
-        self._flat = {id(self.G): FlatGrads(self.G.parameters()), id(self.D): FlatGrads(self.D.parameters())}
+        # flat gradient buffers only where there is an all-reduce to feed: accumulating into pre-assigned .grad views costs one
+        # extra elementwise add per parameter and phase (~200 launches), which a single GPU does not need
+        self.use_flat = world_size > 1 or cfg.force_flat_grads
+        self._flat = {id(self.G): FlatGrads(self.G.parameters()), id(self.D): FlatGrads(self.D.parameters())} if self.use_flat else {}
         for ph in self.phases:
-            ph['flat'] = self._flat[id(ph['module'])]
+            ph['flat'] = self._flat.get(id(ph['module']))
             ph['active'] = None          # which parameters get a gradient in this phase (found on its first run)
         # CUDA-graph state (cfg.cuda_graphs): static inputs, one graph pair per phase, shared memory pool
         self._graphs = None
@@ -297,8 +301,8 @@ class Trainer:
     def _phase_grads(self, ph, real, z):
         """forward + backward of one phase: leaves the gradients in .grad, returns the loss value"""
         opt, module, flat = ph['opt'], ph['module'], ph['flat']
-        if ph['active'] is None:
-            opt.zero_grad(set_to_none=True)        # first run of this phase: let autograd allocate, see who gets a gradient
+        if flat is None or ph['active'] is None:
+            opt.zero_grad(set_to_none=True)        # (first run of this phase:) let autograd allocate, see who gets a gradient
         else:
             flat.arm(ph['active'])
         module.requires_grad_(True)
@@ -313,17 +317,21 @@ class Trainer:
         else:
             val = self.phase_Dreg(real, gain)
         module.requires_grad_(False)
-        if ph['active'] is None:
+        if flat is not None and ph['active'] is None:
             ph['active'] = flat.adopt()
         return val
 
     def _phase_update(self, ph):
-        ph['flat'].nan_to_num_()                   # trainers.py:745-748, all gradients of the module in one launch
+        if ph['flat'] is not None:
+            ph['flat'].nan_to_num_()               # trainers.py:745-748, all gradients of the module in one launch
+        else:
+            nan_to_num_([p.grad for p in ph['module'].parameters() if p.grad is not None], nan=0, posinf=1e5, neginf=-1e5)
         ph['opt'].step()
 
     def run_phase(self, ph, real, z):
         val = self._phase_grads(ph, real, z)
-        ph['flat'].all_reduce_mean()               # trainers.py:887-893 (DistributedDataParallel) as one flat all-reduce
+        if ph['flat'] is not None:
+            ph['flat'].all_reduce_mean()           # trainers.py:887-893 (DistributedDataParallel) as one flat all-reduce
         self._phase_update(ph)
         return val
 

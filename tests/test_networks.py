@@ -125,7 +125,7 @@ def test_cuda_graph_phases_match_golden_and_eager(gold, mode):
     z, meta = gold
     m = MODES[mode]
     torch.backends.cudnn.allow_tf32 = m['tf32']
-    cfg, _, _ = _build(meta, 'cpu', channels_last=True, cuda_graphs=True, lr=0.0, **m['over'])     # lr 0: all four phases see
+    cfg, _, _ = _build(meta, 'cpu', channels_last=True, cuda_graphs=True, lr=0.0, force_flat_grads=(mode != 'strict'), **m['over'])     # lr 0: all four phases see
     tr = training.Trainer(cfg, DEV)                                                                # the golden weights
     _load(z, tr.G, tr.D)
     w0 = [p.detach().clone() for p in list(tr.G.parameters()) + list(tr.D.parameters())]
