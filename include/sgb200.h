@@ -65,6 +65,14 @@ int sgb_upfirdn2d(const void* x, const float* f, void* y, int dtype,
                   int upx, int upy, int downx, int downy, int padx0, int pady0,
                   int flip, float gain, void* stream);
 
+/* The same operator for the case the hot path is dominated by: no resampling (up = down = 1), a filter of at most 4 x 4
+ * taps that is an outer product fy (x) fx (upfirdn2d.setup_filter builds it that way, upfirdn2d.py:105-106), channels_last
+ * tensors with 16-byte channel vectors.  fx / fy are HOST arrays of 4 taps in application order (filter flip and gain applied
+ * by the caller, unused taps zero):  y[oy][ox] = sum_{ty,tx} fy[ty] fx[tx] x[oy - pady0 + ty][ox - padx0 + tx]. */
+int sgb_upfirdn2d_sep(const void* x, const float* fx, const float* fy, void* y, int dtype,
+                      int n, int c, int in_h, int in_w, const int64_t x_strides[4],
+                      int out_h, int out_w, const int64_t y_strides[4], int padx0, int pady0, void* stream);
+
 /* ---- convolution ---------------------------------------------------------------------------
  * Replaces the aten/cuDNN calls of conv2d_gradfix.py:112-114 (conv2d / conv_transpose2d forward, which
  * is also the data gradient of the other one, :125-128) and :143-145 (weight gradient), plus the

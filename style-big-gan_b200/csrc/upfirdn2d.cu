@@ -241,6 +241,103 @@ __global__ void __launch_bounds__(256) upfirdn2d_cl_kernel(UpfirdnParams p, int 
 }
 
 
+template <class T, int UP, int DOWN, int PADPAR>
+__global__ void __launch_bounds__(256) upfirdn2d_cl2_kernel(UpfirdnParams p, int cv_total, int cvb, int txg) {
+  typedef typename Acc<T>::type A;
+  constexpr int VEC = Vec16<T>::N;
+  constexpr int FT = 4, PX = 4, TY = 4;
+  constexpr int NIX = ((PX - 1) * DOWN + FT - 1) / UP + 1;
+  __shared__ float sf[FT * FT];
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  if (tid < FT * FT) {
+    const int ty = tid / FT, tx = tid % FT;
+    float v = 0.f;
+    if (ty < p.fh && tx < p.fw) {
+      const int fy = p.flip ? ty : p.fh - 1 - ty, fx = p.flip ? tx : p.fw - 1 - tx;
+      v = p.f[fy * p.f_sy + fx * p.f_sx] * p.gain;
+    }
+    sf[tid] = v;
+  }
+  __syncthreads();
+
+  const int cchunks = (cv_total + cvb - 1) / cvb;
+  const int n = blockIdx.z / cchunks;
+  const int cv = (blockIdx.z - n * cchunks) * cvb + threadIdx.x;
+  const int ry = threadIdx.y / txg, xg = threadIdx.y - ry * txg;
+  const int oy = blockIdx.y * TY + ry;
+  const int ox0 = (blockIdx.x * txg + xg) * PX;
+  if (cv >= cv_total || oy >= p.out_h || ox0 >= p.out_w) return;
+  const int c0 = cv * VEC;
+
+  A acc[PX][VEC];
+#pragma unroll
+  for (int j = 0; j < PX; j++)
+#pragma unroll
+    for (int e = 0; e < VEC; e++) acc[j][e] = A(0);
+
+  const T* xn = (const T*)p.x + (int64_t)n * p.xs[0] + c0;
+  const int base_y = oy * DOWN - p.pady0;
+  const int ty0 = ((-base_y) % UP + UP) % UP;
+  // first input column any of the PX outputs touches: ceil((ox0*DOWN - padx0) / UP)
+  const int bx = ox0 * DOWN - p.padx0;
+  const int ix_first = (UP == 1) ? bx : ((bx + PADPAR) >> 1);      // UP == 2: bx has parity PADPAR (ox0 is even)
+  const bool interior = ix_first >= 0 && ix_first + NIX <= p.in_w;
+  // all live filter rows are loaded before the first FMA: NR x NIX 128-bit loads in flight per thread (the one-row-at-a-time
+  // form of upfirdn2d_cl_kernel stalls on every row: 45 % of its samples are FFMAs waiting for the row's loads)
+  constexpr int NR = (FT + UP - 1) / UP;
+  Vec16<T> in[NR][NIX];
+  bool live[NR];
+#pragma unroll
+  for (int r = 0; r < NR; r++) {
+    const int ty = ty0 + r * UP;
+    const int iy = (base_y + ty) / UP;
+    live[r] = ty < FT && iy >= 0 && iy < p.in_h;
+    const T* xr = xn + (int64_t)(live[r] ? iy : 0) * p.xs[2];
+    if (interior) {
+      const T* xc = xr + (int64_t)ix_first * p.xs[3];
+#pragma unroll
+      for (int i = 0; i < NIX; i++) in[r][i].raw = live[r] ? __ldg((const uint4*)(xc + (int64_t)i * p.xs[3])) : make_uint4(0, 0, 0, 0);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NIX; i++) {
+        const int ix = ix_first + i;
+        in[r][i].raw = (live[r] && ix >= 0 && ix < p.in_w) ? __ldg((const uint4*)(xr + (int64_t)ix * p.xs[3])) : make_uint4(0, 0, 0, 0);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < NR; r++) {
+    const int ty = ty0 + r * UP;
+    if (ty >= FT) continue;
+    const float4 fr = *(const float4*)(sf + ty * FT);
+    const float frow[4] = {fr.x, fr.y, fr.z, fr.w};
+#pragma unroll
+    for (int j = 0; j < PX; j++) {
+#pragma unroll
+      for (int tx = 0; tx < FT; tx++) {
+        const int rel = j * DOWN + tx - ((UP == 2) ? PADPAR : 0);
+        if (UP == 2 && (rel & 1)) continue;
+        const int i = rel / UP;
+        if (i < 0 || i >= NIX) continue;
+        const A fv = A(frow[tx]);
+#pragma unroll
+        for (int e = 0; e < VEC; e++) acc[j][e] += to_acc<T>(in[r][i].v[e]) * fv;
+      }
+    }
+  }
+  T* yp = (T*)p.y + (int64_t)n * p.ys[0] + (int64_t)oy * p.ys[2] + c0;
+#pragma unroll
+  for (int j = 0; j < PX; j++) {
+    if (ox0 + j >= p.out_w) break;
+    Vec16<T> o;
+#pragma unroll
+    for (int e = 0; e < VEC; e++) o.v[e] = from_acc<T>(acc[j][e]);
+    *(uint4*)(yp + (int64_t)(ox0 + j) * p.ys[3]) = o.raw;
+  }
+}
+
+
+
 // ------------------------------------------------------------------------------------------------------
 // channels_last STRIP kernel (the default for channels_last tensors, filters up to 4x4, (up, down) in {(1,1),(2,1),(1,2)}).
 // A thread owns 16 bytes of channels x PX consecutive output columns and walks DOWN a strip of `rows` output rows.  Every
@@ -429,6 +526,109 @@ __global__ void __launch_bounds__(256) upfirdn2d_strip_kernel(UpfirdnParams p, i
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// Separable FIR, no resampling (the two big forms of the hot path: after the transposed convolution of an up-sampling layer
+// and in front of the strided convolution of a down-sampling layer), channels_last.  The host has factored the 4 x 4 filter
+// into fy (x) fx (setup_filter builds it as an outer product; sgb200/ops/upfirdn2d.py checks and caches that per filter tensor).
+// A thread owns 16 bytes of channels x PX output columns and walks down a strip of output rows: every input row is loaded
+// and converted ONCE, filtered horizontally (4 FMAs per element) into a ring of the last four rows, and an output row is the
+// vertical 4-tap combination of the ring (4 FMAs per element): 8 FMAs and one conversion per output element instead of 16 + 7
+// in upfirdn2d_cl_kernel.  That matters for 16-bit tensors, where the stencil is bound by instruction issue, not by HBM
+// (ncu, profiles/README.md: fp16 [4,32,1025,1025] at 25 % of DRAM throughput with 58 % of the issue slots busy).
+struct FirSepParams {
+  const void* x; void* y;
+  int n, c, in_h, in_w, out_h, out_w;
+  int64_t xs[4], ys[4];
+  int padx0, pady0;
+  float fx[4], fy[4];          // taps in application order: y[oy][ox] = sum fy[ty] fx[tx] x[oy - pady0 + ty][ox - padx0 + tx]
+  int cv_total, cvb, xgs, rows;
+};
+
+template <class T>
+__global__ void __launch_bounds__(256, 2) fir_sep_strip_kernel(FirSepParams p) {
+  constexpr int VEC = Vec16<T>::N;
+  constexpr int PX = (VEC == 4) ? 4 : 2;
+  constexpr int NIX = PX + 3;
+  const int cchunks = (p.cv_total + p.cvb - 1) / p.cvb;
+  const int n = blockIdx.z / cchunks;
+  const int cv = (blockIdx.z - n * cchunks) * p.cvb + threadIdx.x;
+  const int oy0 = blockIdx.y * p.rows;
+  const int ox0 = (blockIdx.x * p.xgs + threadIdx.y) * PX;
+  if (cv >= p.cv_total || ox0 >= p.out_w) return;
+  const int R = min(p.rows, p.out_h - oy0);
+  const int K = R + 3;
+  const int iy0 = oy0 - p.pady0;
+  const int ix_first = ox0 - p.padx0;
+  const bool interior = ix_first >= 0 && ix_first + NIX <= p.in_w;
+  const T* xn = (const T*)p.x + (int64_t)n * p.xs[0] + cv * VEC;
+  T* yn = (T*)p.y + (int64_t)n * p.ys[0] + cv * VEC;
+  const float fx0 = p.fx[0], fx1 = p.fx[1], fx2 = p.fx[2], fx3 = p.fx[3];
+  const float fy0 = p.fy[0], fy1 = p.fy[1], fy2 = p.fy[2], fy3 = p.fy[3];
+
+  float h[4][PX][VEC];          // ring: horizontally filtered input rows k - 3 ... k
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+#pragma unroll
+    for (int j = 0; j < PX; j++)
+#pragma unroll
+      for (int e = 0; e < VEC; e++) h[r][j][e] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += 4) {
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
+      const int k = k0 + kk;
+      if (k < K) {
+        const int iy = iy0 + k;
+        float v[NIX][VEC];
+        if (iy >= 0 && iy < p.in_h) {
+          const T* xr = xn + (int64_t)iy * p.xs[2];
+          Vec16<T> in[NIX];
+          if (interior) {
+            const T* xc = xr + (int64_t)ix_first * p.xs[3];
+#pragma unroll
+            for (int i = 0; i < NIX; i++) in[i].raw = __ldg((const uint4*)(xc + (int64_t)i * p.xs[3]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < NIX; i++) {
+              const int ix = ix_first + i;
+              in[i].raw = (ix >= 0 && ix < p.in_w) ? __ldg((const uint4*)(xr + (int64_t)ix * p.xs[3])) : make_uint4(0, 0, 0, 0);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < NIX; i++)
+#pragma unroll
+            for (int e = 0; e < VEC; e++) v[i][e] = to_acc<T>(in[i].v[e]);
+#pragma unroll
+          for (int j = 0; j < PX; j++)
+#pragma unroll
+            for (int e = 0; e < VEC; e++)
+              h[kk][j][e] = v[j][e] * fx0 + v[j + 1][e] * fx1 + v[j + 2][e] * fx2 + v[j + 3][e] * fx3;
+        } else {
+#pragma unroll
+          for (int j = 0; j < PX; j++)
+#pragma unroll
+            for (int e = 0; e < VEC; e++) h[kk][j][e] = 0.f;
+        }
+        const int jr = k - 3;                 // output row completed by input row k: rows k-3 .. k sit in slots (kk+1..kk+4) & 3
+        if (jr >= 0 && jr < R) {
+          T* yp = yn + (int64_t)(oy0 + jr) * p.ys[2];
+#pragma unroll
+          for (int j = 0; j < PX; j++) {
+            if (ox0 + j < p.out_w) {
+              Vec16<T> o;
+#pragma unroll
+              for (int e = 0; e < VEC; e++)
+                o.v[e] = from_acc<T>(h[(kk + 1) & 3][j][e] * fy0 + h[(kk + 2) & 3][j][e] * fy1 + h[(kk + 3) & 3][j][e] * fy2 + h[kk][j][e] * fy3);
+              *(uint4*)(yp + (int64_t)(ox0 + j) * p.ys[3]) = o.raw;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
 }  // namespace sgb
 
 using namespace sgb;
@@ -495,6 +695,15 @@ static int launch_upfirdn(const UpfirdnParams& p, cudaStream_t s) {
     if (gy <= 65535 && gz <= 65535) {
       dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)gz), block(cvb, 256 / cvb);
       const int pp = p.padx0 & 1;
+      static const int v2 = [] { const char* e = getenv("SGB_FIR_V2"); return e ? atoi(e) : 1; }();
+      // measured (profiles/README.md): hoisting all loads wins for up = 2 (2 live filter rows, 48-64 registers: fp32
+      // [32,64,128,128] 0.148 -> 0.124 ms = 5.4 TB/s) and loses for the 4-row forms (132-255 registers, occupancy)
+      if (v2 && p.upx == 2) {
+        if (pp == 0) upfirdn2d_cl2_kernel<T, 2, 1, 0><<<grid, block, 0, s>>>(p, cv_total, cvb, txg);
+        else         upfirdn2d_cl2_kernel<T, 2, 1, 1><<<grid, block, 0, s>>>(p, cv_total, cvb, txg);
+        SGB_LAUNCH_CHECK();
+        return 0;
+      }
       if (p.upx == 1 && p.downx == 1)      upfirdn2d_cl_kernel<T, 1, 1, 0><<<grid, block, 0, s>>>(p, cv_total, cvb, txg);
       else if (p.upx == 2 && pp == 0)      upfirdn2d_cl_kernel<T, 2, 1, 0><<<grid, block, 0, s>>>(p, cv_total, cvb, txg);
       else if (p.upx == 2)                 upfirdn2d_cl_kernel<T, 2, 1, 1><<<grid, block, 0, s>>>(p, cv_total, cvb, txg);
@@ -532,5 +741,40 @@ extern "C" int sgb_upfirdn2d(const void* x, const float* f, void* y, int dtype,
   p.c_fast = (y_strides[1] == 1 && c > 1) ? 1 : 0;
   cudaStream_t s = (cudaStream_t)stream;
   SGB_DISPATCH_DTYPE(dtype, return launch_upfirdn<T>(p, s));
+  return 0;
+}
+
+/* upfirdn2d without resampling for a 4 x 4 (or smaller) filter the caller has factored into fy (x) fx -- see fir_sep_strip_kernel.
+ * fx / fy: HOST arrays of 4 taps in application order (flip and gain already applied; unused taps zero). */
+extern "C" int sgb_upfirdn2d_sep(const void* x, const float* fx, const float* fy, void* y, int dtype,
+                                 int n, int c, int in_h, int in_w, const int64_t x_strides[4],
+                                 int out_h, int out_w, const int64_t y_strides[4], int padx0, int pady0, void* stream) {
+  SGB_REQUIRE(x && fx && fy && y, "x, fx, fy and y must not be NULL");
+  SGB_REQUIRE(dtype == SGB_F32 || dtype == SGB_F16 || dtype == SGB_BF16, "unsupported dtype");
+  SGB_REQUIRE(n >= 0 && c >= 1 && in_h >= 1 && in_w >= 1 && out_h >= 1 && out_w >= 1, "bad size");
+  if (n == 0) return 0;
+  const int vec = dtype == SGB_F32 ? 4 : 8;
+  SGB_REQUIRE(x_strides[1] == 1 && y_strides[1] == 1 && c % vec == 0 && aligned16(x) && aligned16(y), "needs channels_last tensors with 16-byte channel vectors");
+  for (int i : {0, 2, 3}) SGB_REQUIRE(x_strides[i] % vec == 0 && y_strides[i] % vec == 0, "strides must keep 16-byte alignment");
+  FirSepParams p;
+  p.x = x; p.y = y; p.n = n; p.c = c; p.in_h = in_h; p.in_w = in_w; p.out_h = out_h; p.out_w = out_w;
+  for (int i = 0; i < 4; i++) { p.xs[i] = x_strides[i]; p.ys[i] = y_strides[i]; p.fx[i] = fx[i]; p.fy[i] = fy[i]; }
+  p.padx0 = padx0; p.pady0 = pady0;
+  const int PX = vec == 4 ? 4 : 2;
+  p.cv_total = c / vec;
+  int cvb = 1; while (cvb < p.cv_total && cvb < 32) cvb <<= 1;
+  p.cvb = cvb; p.xgs = 256 / cvb;
+  const int64_t gx = ceil_div(out_w, p.xgs * PX), gz = (int64_t)n * ceil_div(p.cv_total, cvb);
+  int rows = out_h >= 128 ? 32 : (out_h >= 32 ? 16 : 8);
+  while (rows > 8 && gx * ceil_div(out_h, rows) * gz < 4 * (int64_t)num_sms()) rows >>= 1;
+  p.rows = rows;
+  const int64_t gy = ceil_div(out_h, rows);
+  SGB_REQUIRE(gy <= 65535 && gz <= 65535, "grid too large");
+  dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)gz), block(cvb, p.xgs);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == SGB_F32) fir_sep_strip_kernel<float><<<grid, block, 0, s>>>(p);
+  else if (dtype == SGB_F16) fir_sep_strip_kernel<__half><<<grid, block, 0, s>>>(p);
+  else fir_sep_strip_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(p);
+  SGB_LAUNCH_CHECK();
   return 0;
 }

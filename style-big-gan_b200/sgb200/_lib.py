@@ -46,6 +46,8 @@ SIGNATURES = {
     'sgb_sum_to_channel': (_int, [_vp, _vp, _int, _i64, _i64, _i64, _vp]),
     'sgb_upfirdn2d': (_int, [_vp, _vp, _vp, _int, _int, _int, _int, _int, _c.POINTER(_i64), _int, _int, _c.POINTER(_i64),
                              _int, _int, _i64, _i64, _int, _int, _int, _int, _int, _int, _int, _flt, _vp]),
+    'sgb_upfirdn2d_sep': (_int, [_vp, _c.POINTER(_flt), _c.POINTER(_flt), _vp, _int, _int, _int, _int, _int, _c.POINTER(_i64), _int, _int,
+                          _c.POINTER(_i64), _int, _int, _vp]),
     'sgb_conv2d_forward': (_int, [_c.POINTER(ConvDesc), _vp, _vp, _vp, _vp]),
     'sgb_conv2d_wgrad': (_int, [_c.POINTER(ConvDesc), _vp, _vp, _vp, _vp]),
     'sgb_conv2d_uses_tensor_cores': (_int, [_c.POINTER(ConvDesc)]),

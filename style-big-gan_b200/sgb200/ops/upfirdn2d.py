@@ -6,7 +6,10 @@ private helpers `_parse_padding` / `_get_filter_size` / `_parse_scaling` that `c
 Gradients of arbitrary order: the backward of the op is the op itself with up/down swapped and the filter
 flipped (reference :246-264).
 """
+import ctypes
 import math
+import os
+import weakref
 
 import numpy as np
 import torch
@@ -69,6 +72,42 @@ def setup_filter(f, device=torch.device('cpu'), normalize=True, flip_filter=Fals
     return f.to(device=device)
 
 
+separable_kernel = os.environ.get('SGB_FIR_SEP', '1') != '0'     # A/B switch: the separable strip kernel for plain FIR passes
+_sep_cache = {}     # id(filter tensor) -> (weakref to it, version, (row, col) or None)
+
+
+def _separable_taps(f2d, flip, gain):
+    """(fx, fy) as 4-tap host lists in application order if the (at most 4 x 4) filter is an outer product, else None.
+    The factorisation needs the filter values on the host: one device->host copy per filter TENSOR (module buffers such as
+    `resample_filter` are long-lived), never during CUDA-graph capture (an unseen filter then takes the general kernel)."""
+    fh, fw = f2d.shape
+    if fh > 4 or fw > 4:
+        return None
+    hit = _sep_cache.get(id(f2d))
+    if hit is not None and (hit[0]() is not f2d or hit[1] != f2d._version):
+        hit = None
+    if hit is None:
+        if torch.cuda.is_current_stream_capturing():
+            return None
+        a = f2d.detach().to('cpu', torch.float64).numpy()
+        fac = None
+        r0, c0 = np.unravel_index(np.argmax(np.abs(a)), a.shape)
+        if a[r0, c0] != 0:
+            row, col = a[r0, :].copy(), a[:, c0] / a[r0, c0]
+            if np.abs(np.outer(col, row) - a).max() <= 1e-7 * np.abs(a[r0, c0]):
+                fac = (row, col)
+        key = id(f2d)
+        hit = (weakref.ref(f2d, lambda _r, k=key: _sep_cache.pop(k, None)), f2d._version, fac)
+        _sep_cache[key] = hit
+    if hit[2] is None:
+        return None
+    row, col = hit[2]
+    # application order (csrc/upfirdn2d.cu): tap t multiplies the filter entry t if flip_filter else size-1-t; unused taps are zero
+    fx = [float(row[t] if flip else row[fw - 1 - t]) * float(gain) if t < fw else 0.0 for t in range(4)]
+    fy = [float(col[t] if flip else col[fh - 1 - t]) if t < fh else 0.0 for t in range(4)]
+    return fx, fy
+
+
 def _run(x, f2d, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain):
     """One sgb_upfirdn2d launch with a 2-D fp32 filter (any strides)."""
     n, c, ih, iw = x.shape
@@ -80,6 +119,19 @@ def _run(x, f2d, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain)
     y = torch.empty([n, c, oh, ow], dtype=x.dtype, device=x.device, memory_format=_lib.out_format(x))
     if y.numel() == 0:
         return y
+    vec = 16 // x.element_size()
+    if (separable_kernel and upx == upy == downx == downy == 1 and x.dtype in (torch.float32, torch.float16, torch.bfloat16)
+            and c % vec == 0 and _lib.is_channels_last(x) and _lib.is_channels_last(y) and x.data_ptr() % 16 == 0
+            and all(st % vec == 0 for i, st in enumerate(x.stride()) if i != 1)):
+        taps = _separable_taps(f2d, flip, gain)
+        if taps is not None:
+            fx = (ctypes.c_float * 4)(*taps[0])
+            fy = (ctypes.c_float * 4)(*taps[1])
+            with torch.cuda.device(x.device), _lib.prof('upfirdn2d', 0.0, (x.numel() + y.numel()) * x.element_size()):
+                rc = _lib.lib().sgb_upfirdn2d_sep(_lib.ptr(x), fx, fy, _lib.ptr(y), _lib.dtype_code(x), n, c, ih, iw, _lib.strides4(x),
+                                                  oh, ow, _lib.strides4(y), padx0, pady0, _lib.stream_ptr(x.device))
+            _lib.check(rc, 'upfirdn2d_sep')
+            return y
     with torch.cuda.device(x.device), _lib.prof('upfirdn2d', 0.0, (x.numel() + y.numel()) * x.element_size()):
         rc = _lib.lib().sgb_upfirdn2d(_lib.ptr(x), _lib.ptr(f2d), _lib.ptr(y), _lib.dtype_code(x),
                                       n, c, ih, iw, _lib.strides4(x), oh, ow, _lib.strides4(y),

@@ -145,12 +145,14 @@ class FlatGradAllReduce:
 
 
 class FlatGrads:
-    """The gradients of a parameter list as views of ONE flat fp32 buffer: autograd accumulates into them in place, so the
-    per-phase bookkeeping of the reference loop (trainers.py:733,745-748,887-893) becomes four launches that are all legal
-    inside a CUDA graph: one memset (zero_grad), one NCCL all-reduce of the flat buffer (what DistributedDataParallel's
-    bucketed all-reduce amounts to), one scale, one nan_to_num -- instead of a torch.cat, an all-reduce between two graphs
-    and ~200 per-tensor copies.  Parameters that receive NO gradient in a phase keep `grad = None` there (`active` mask,
-    discovered on the phase's first run), so Adam skips them exactly as in the reference."""
+    """The gradients of a parameter list gathered into ONE flat fp32 buffer, so that the per-phase bookkeeping of the reference
+    loop (trainers.py:745-748,887-893) is a handful of launches that are all legal inside a CUDA graph: one multi-tensor copy
+    of the gradients autograd produced into the buffer, one NCCL all-reduce of the buffer (what DistributedDataParallel's
+    bucketed all-reduce amounts to), one scale, one nan_to_num -- instead of a torch.cat, an all-reduce between two graphs and
+    ~200 per-tensor copies.  After `gather()` every `.grad` is a view of the buffer, which is what the optimizer reads.
+    (Pointing `.grad` at the views BEFORE backward would save the copy but makes autograd accumulate in place: one extra
+    elementwise add per parameter, ~200 launches per phase, measured slower.)  Parameters that receive no gradient in a
+    phase keep `grad = None`, so Adam skips them exactly as in the reference."""
 
     def __init__(self, params, group=None):
         self.params = [p for p in params]
@@ -164,23 +166,20 @@ class FlatGrads:
             self.views.append(self.flat[off:off + p.numel()].view(p.shape))
             off += p.numel()
 
-    def arm(self, active):
-        """zero the buffer and point .grad of the active parameters at their views (others: None)"""
-        self.flat.zero_()
-        for p, v, a in zip(self.params, self.views, active):
-            p.grad = v if a else None
-
-    def adopt(self):
-        """after a classic backward (grads allocated by autograd): copy them into the views; returns the active mask"""
-        active = []
-        self.flat.zero_()
+    def gather(self):
+        """copy the gradients autograd left in .grad into the flat buffer (one multi-tensor launch) and re-point .grad at the views"""
+        src, dst = [], []
         for p, v in zip(self.params, self.views):
-            active.append(p.grad is not None)
+            if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
+                src.append(p.grad)
+                dst.append(v)
+        if len(src) < len(self.params):
+            self.flat.zero_()                      # slots of parameters without a gradient must not carry stale values into the sum
+        if src:
+            torch._foreach_copy_(dst, src)
+        for p, v in zip(self.params, self.views):
             if p.grad is not None:
-                if p.grad.data_ptr() != v.data_ptr():
-                    v.copy_(p.grad)
                 p.grad = v
-        return active
 
     def all_reduce_mean(self):
         if not (dist.is_available() and dist.is_initialized()):
@@ -232,7 +231,6 @@ class Trainer:
         self._flat = {id(self.G): FlatGrads(self.G.parameters()), id(self.D): FlatGrads(self.D.parameters())} if self.use_flat else {}
         for ph in self.phases:
             ph['flat'] = self._flat.get(id(ph['module']))
-            ph['active'] = None          # which parameters get a gradient in this phase (found on its first run)
         # CUDA-graph state (cfg.cuda_graphs): static inputs, one graph pair per phase, shared memory pool
         self._graphs = None
         self.replayed_launches = 0      # libsgb200 kernel launches executed through graph replays
@@ -301,10 +299,7 @@ class Trainer:
     def _phase_grads(self, ph, real, z):
         """forward + backward of one phase: leaves the gradients in .grad, returns the loss value"""
         opt, module, flat = ph['opt'], ph['module'], ph['flat']
-        if flat is None or ph['active'] is None:
-            opt.zero_grad(set_to_none=True)        # (first run of this phase:) let autograd allocate, see who gets a gradient
-        else:
-            flat.arm(ph['active'])
+        opt.zero_grad(set_to_none=True)
         module.requires_grad_(True)
         gain = ph['interval']
         name = ph['name']
@@ -317,8 +312,8 @@ class Trainer:
         else:
             val = self.phase_Dreg(real, gain)
         module.requires_grad_(False)
-        if flat is not None and ph['active'] is None:
-            ph['active'] = flat.adopt()
+        if flat is not None:
+            flat.gather()
         return val
 
     def _phase_update(self, ph):

@@ -34,14 +34,15 @@ def _worker(rank, world, port, q):
     ok &= torch.allclose(params[0].grad, torch.full((3, 4), 1.5))
     ok &= torch.allclose(params[1].grad, torch.arange(5, dtype=torch.float32) * 1.5)
     ok &= params[2].grad is None
-    # FlatGrads: gradients as views of one flat buffer, averaged in place with one all-reduce (the in-graph path of
-    # sgb200.training.Trainer); a parameter that is inactive in the phase keeps grad None and its slot stays zero
+    # FlatGrads: the gradients gathered into one flat buffer and averaged in place with one all-reduce (the in-graph path of
+    # sgb200.training.Trainer); a parameter without a gradient keeps grad None and its slot stays zero
     from sgb200.training import FlatGrads
     ps = [torch.nn.Parameter(torch.ones(3, 4)), torch.nn.Parameter(torch.ones(5)), torch.nn.Parameter(torch.ones(2, 2))]
     fg = FlatGrads(ps)
-    fg.arm([True, True, False])
+    fg.flat.fill_(7.0)                                               # stale values from an earlier phase
     ((ps[0] * (rank + 1)).sum() + (ps[1] * ps[1] * (rank + 2)).sum()).backward()
-    ok &= ps[0].grad.data_ptr() == fg.views[0].data_ptr()           # autograd accumulated in place
+    fg.gather()
+    ok &= ps[0].grad.data_ptr() == fg.views[0].data_ptr()           # .grad now aliases the flat buffer
     ok &= fg.all_reduce_mean() == 21
     ok &= torch.allclose(ps[0].grad, torch.full((3, 4), 1.5)) and torch.allclose(ps[1].grad, torch.full((5,), 5.0))
     ok &= ps[2].grad is None and float(fg.flat[17:].abs().sum()) == 0.0
