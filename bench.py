@@ -291,7 +291,7 @@ def measure(ctx, args, workload, fp32_mode, steps, e2e, roofline, clocks, breakd
     world, rank, device, peaks = ctx['world'], ctx['rank'], ctx['device'], ctx['peaks']
     torch.backends.cudnn.allow_tf32 = (fp32_mode == 'tf32')
     torch.backends.cuda.matmul.allow_tf32 = (fp32_mode == 'tf32')
-    cfg = workload_config(workload, cuda_graphs=not args.no_graphs)
+    cfg = workload_config(workload, cuda_graphs=not args.no_graphs, allreduce_in_graph=os.environ.get('SGB_ALLREDUCE_IN_GRAPH', '1') != '0')
     tr = training.Trainer(cfg, device, rank=rank, world_size=world)
     R, N = cfg.img_resolution, cfg.batch_gpu
     host_real = torch.randint(0, 256, [N, cfg.img_channels, R, R], dtype=torch.uint8).pin_memory()

@@ -17,14 +17,15 @@ PFN_encodeTiled tma_encode_fn() {
 
 // which convolutions take the TMA kernel: stride 1 (conv2d and conv_transpose2d), kernels up to 3x3, fp16 / fp32-as-TF32,
 // images of at least 32 rows (smaller ones: conv_halo_kernel's tiles straddle images, per-image tiles would be mostly padding),
-// a channel count whose bytes are a multiple of 16 (tensor-map strides), no fused epilogue.
+// a channel count whose bytes are a multiple of 16 (tensor-map strides); fused epilogue: linear / lrelu.
 // SGB_TMA: 1 (default) = on, 0 = off (A/B)
 static bool tma_geometry_ok(const sgb_conv_desc* d) {
   static const int on = [] { const char* e = getenv("SGB_TMA"); return e ? atoi(e) : 1; }();
   if (!on) return false;
   if (d->dtype != SGB_F16 && d->dtype != SGB_F32) return false;
   if (d->stride != 1 || d->kh > 3 || d->kw > 3 || d->groups != 1) return false;
-  if (d->out_scale || d->noise || d->bias || d->act != 0) return false;
+  if (d->act != 0 && d->act != SGB_ACT_LINEAR && d->act != SGB_ACT_LRELU) return false;
+  if (d->bias && d->act == 0) return false;
   static const int force_g = [] { const char* e = getenv("SGB_TMA_FORCE"); return e ? atoi(e) : 0; }();
   if ((d->out_h < 32 || d->out_w < 32) && !force_g) return false;
   if (!d->transposed) { if (d->out_h != d->in_h + 2 * d->pad_y - d->kh + 1 || d->out_w != d->in_w + 2 * d->pad_x - d->kw + 1) return false; }

@@ -290,6 +290,14 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_c
     // =========================== epilogue (warps 0-3) ===========================
     const int m = threadIdx.x;                         // TMEM lane = tile row
     uint8_t* stg = smem + p.stg_off + warp * (32 * PITCH);
+    // fused tail (sgb_conv_desc.out_scale / noise / bias / act): y = clamp(act(acc * out_scale[n,o] + noise[n,oy,ox] + bias[o]) * gain).
+    // The per-channel vectors of the tile are staged once per tile in a per-warp slice of shared memory and read back as
+    // broadcast float4 loads (conv_halo_kernel fetched them with one __ldg per element, which made its epilogue the bottleneck).
+    float* s_sc = (float*)(smem + p.stg_off + 4 * 32 * PITCH) + warp * (2 * BN);
+    float* s_bs = s_sc + BN;
+    const bool fused = d.out_scale != nullptr || d.noise != nullptr || d.act != 0;
+    const bool has_act = d.act != 0;
+    const float alpha = d.alpha, gain = d.gain, clampv = d.clamp;
     const int q_chunk = lane % LPP;
     const int q_pix = lane / LPP;
     int li = 0;
@@ -311,12 +319,21 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_c
         qox[k] = ox0 + (mm & 7);
         yoff[k] = (oy2 < d.out_h) ? (ybase + (int64_t)oy2 * d.y_strides[2]) : -1;
       }
+      if (fused) {
+        for (int i = lane; i < BN; i += 32) {
+          const int o = o_base + i;
+          s_sc[i] = (d.out_scale && o < d.co) ? ((const float*)d.out_scale)[(int64_t)n * d.co + o] : 1.f;
+          s_bs[i] = (d.bias && o < d.co) ? to_acc<T>(((const T*)d.bias)[o]) : 0.f;
+        }
+        __syncwarp();
+      }
       mbar_wait(smem_u32(&acc_full[buf]), fph);
       tc_fence_after();
 #pragma unroll 1
       for (int g = 0; g < GT; g++) {
         const int ox = oxr + g * TMA_TILE_W;
         const bool row_ok = oy < d.out_h && ox < d.out_w;
+        const float nz = (d.noise && row_ok) ? ((const float*)d.noise)[((int64_t)n * d.out_h + oy) * d.out_w + ox] : 0.f;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * (NACC * BN) + g * BN;
         T* yrow = (T*)p.y + ybase + (int64_t)oy * d.y_strides[2] + (int64_t)ox * d.y_strides[3];
 #pragma unroll 1
@@ -326,19 +343,38 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_c
             const int cc = cc0 + cs;
             uint32_t acc[16];
             tmem_ld16(lane_addr + cc, acc);
+            float val[16];
+#pragma unroll
+            for (int e = 0; e < 16; e++) val[e] = __uint_as_float(acc[e]);
+            if (fused) {
+#pragma unroll
+              for (int q4 = 0; q4 < 4; q4++) {
+                const float4 sc4 = *(const float4*)(s_sc + cc + q4 * 4), bs4 = *(const float4*)(s_bs + cc + q4 * 4);
+                const float scv[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, bsv[4] = {bs4.x, bs4.y, bs4.z, bs4.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                  float v = val[q4 * 4 + e] * scv[e] + nz + bsv[e];
+                  if (has_act) {
+                    v = (v > 0.f ? v : v * alpha) * gain;                        // explicit compares: NaN propagates like torch
+                    if (clampv >= 0.f) v = v < -clampv ? -clampv : (v > clampv ? clampv : v);
+                  }
+                  val[q4 * 4 + e] = v;
+                }
+              }
+            }
             if (p.vec_store) {
 #pragma unroll
               for (int q = 0; q < 16 / TC; q++) {
                 Vec16<T> pk;
 #pragma unroll
-                for (int e = 0; e < TC; e++) pk.v[e] = from_acc<T>(__uint_as_float(acc[q * TC + e]));
+                for (int e = 0; e < TC; e++) pk.v[e] = from_acc<T>(val[q * TC + e]);
                 *(uint4*)(stg + lane * PITCH + cs * (int)sizeof(T) + q * 16) = pk.raw;
               }
             } else if (row_ok) {
 #pragma unroll
               for (int e = 0; e < 16; e++) {
                 const int o = o_base + cc + e;
-                if (o < d.co) yrow[(int64_t)o * d.y_strides[1]] = from_acc<T>(__uint_as_float(acc[e]));
+                if (o < d.co) yrow[(int64_t)o * d.y_strides[1]] = from_acc<T>(val[e]);
               }
             }
           }
@@ -408,6 +444,8 @@ int launch_tma(const sgb_conv_desc* d, const void* x, const void* w, void* y, cu
   p.pass = (d->in_scale != nullptr || (KIND == 2 && !no_round)) ? 1 : 0;
   p.bo_mode = bo_mode;
   SGB_REQUIRE(aligned16(x) && aligned16(d->workspace), "x and workspace must be 16-byte aligned");
+  SGB_REQUIRE(d->act == 0 || d->act == SGB_ACT_LINEAR || d->act == SGB_ACT_LRELU, "fused epilogue supports linear and lrelu only");
+  if (d->act == SGB_ACT_LINEAR) p.d.alpha = 1.f;
 
   // tensor map of x: dims (innermost first) {C, W, H, N}, byte strides of W, H, N; box {KB bytes of channels, HC, HR, 1}
   CUtensorMap tm;
@@ -425,7 +463,7 @@ int launch_tma(const sgb_conv_desc* d, const void* x, const void* w, void* y, cu
 
   if (int r = pack_weights_umma(d, w, BN, s)) return r;
   const int budget = 223 * 1024;                    // 226 KB of dynamic shared memory - 1 KB alignment slack - margin
-  const int stg_bytes = 4 * 32 * PITCH;
+  const int stg_bytes = 4 * 32 * PITCH + 4 * 2 * BN * (int)sizeof(float);      // store slabs + per-warp scale / bias vectors
   const int b_tap = BN * KB;
   int sa = 0, sb = 0, tps = 1;
   // few channels: the whole packed weight tensor stays in shared memory (no weight stream, no b_full / b_empty hand-shakes)

@@ -189,8 +189,8 @@ __global__ void __launch_bounds__(256) scale_bias_act_kernel(TailParams p) {
         const float sc = p.out_scale ? __ldg(p.out_scale + n * p.c + c0 + j) : 1.f;
         const float b = p.bias ? to_acc<T>(((const T*)p.bias)[c0 + j]) : 0.f;
         float t = fmaf(to_acc<T>(in.v[j]), sc, nz + b);
-        t = fmaxf(t, t * p.alpha) * p.gain;
-        t = fminf(fmaxf(t, -e_clamp), e_clamp);
+        t = (t > 0.f ? t : t * p.alpha) * p.gain;                       // explicit compares: a NaN pre-activation stays NaN, as in
+        t = t < -e_clamp ? -e_clamp : (t > e_clamp ? e_clamp : t);      // bias_act.cu and torch.clamp (fmaxf / fminf drop NaN operands)
         out.v[j] = from_acc<T>(t);
       }
       st_stream((uint4*)p.y + v, out.raw);

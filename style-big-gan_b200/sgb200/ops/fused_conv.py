@@ -24,11 +24,18 @@ from . import conv2d_gradfix as _cg
 from . import fma as _fma
 
 _ACT_ID = {'linear': 1, 'lrelu': 3}
-# Measured on B200 (ffhq256, batch 32, TF32; profiles/README.md): with the present epilogue the fused forward costs the
-# convolution kernel more than the activation-sized passes it removes (78.7 ms/step un-fused vs 93.8 fused: the four
-# epilogue warps become the bottleneck), so the un-fused composition is the default; `enabled = True` or
-# SGB_FUSED_CONV=1 switches the fused kernels on (tests cover both).
-enabled = os.environ.get('SGB_FUSED_CONV', '0') == '1'
+# Which convolutions run the tail in their epilogue (SGB_FUSED_CONV):
+#   '0' (default)  none: every convolution is followed by the ONE-pass tail kernel (sgb_scale_bias_act / bias_act)
+#   'tma'          those that take the TMA-staged kernel (csrc/conv_tma.cuh), whose epilogue stages the per-channel vectors of a
+#                  tile in shared memory once
+#   '1'            every tensor-core convolution (tests, A/B)
+# Measured on a B200 (profiles/README.md): the fused forward is SLOWER than the pass it removes in both kernels -- round 1,
+# conv_halo_kernel (one __ldg per element in the epilogue): 93.8 vs 78.7 ms/step; round 2, conv_tma_kernel (vectors staged in
+# shared memory): ffhq256 76.6 vs 73.0 ms/step, config-f 1024 64.0 vs 59.3.  With the MMA issue cost cut 3x (warp-uniform
+# issue) the four epilogue warps are the critical path of the few-channel layers, and every instruction added to them shows.
+enabled = os.environ.get('SGB_FUSED_CONV', '0')
+if enabled in ('0', '1'):
+    enabled = enabled == '1'
 
 
 def _noise4(noise, n, h, w):
@@ -37,6 +44,14 @@ def _noise4(noise, n, h, w):
     if noise.ndim < 4 or noise.shape[0] != n:
         noise = noise.expand(n, 1, h, w)
     return noise
+
+
+def _conv_then_tail(x, w, b, styles, dcoefs, noise, stride, padding, flip_weight, act, alpha, gain, clamp):
+    """convolution followed by the one-pass tail (differentiable; the default route of layers that are not fused)"""
+    y = _cg.conv2d(x, w, stride=stride, padding=padding, flip_weight=(not flip_weight), in_scale=styles)
+    if dcoefs is None and noise is None:
+        return _ba.bias_act(y, b, act=act, alpha=alpha, gain=gain, clamp=clamp)
+    return scale_bias_act(y, b, dcoefs, noise, act=act, alpha=alpha, gain=gain, clamp=clamp)
 
 
 def _unfused(x, w, b, styles, dcoefs, noise, stride, padding, flip_weight, act, alpha, gain, clamp):
@@ -50,8 +65,8 @@ def _unfused(x, w, b, styles, dcoefs, noise, stride, padding, flip_weight, act, 
     return _ba.bias_act(y, b, act=act, alpha=alpha, gain=gain, clamp=clamp)
 
 
-def _fusable(x, w, b, styles, dcoefs, noise, act):
-    if not enabled or act not in _ACT_ID or not x.is_cuda or x.ndim != 4 or x.numel() == 0:
+def _fusable(x, w, b, styles, dcoefs, noise, act, gain=1.0):
+    if not enabled or gain == 0 or act not in _ACT_ID or not x.is_cuda or x.ndim != 4 or x.numel() == 0:
         return False
     mult = _cg._tc_multiple(x, 1)
     if not mult or x.shape[1] % mult != 0:
@@ -69,8 +84,8 @@ def conv2d_bias_act(x, w, b=None, *, stride=1, padding=0, flip_weight=True, styl
     gain = float(gain if gain is not None else spec.def_gain)
     clamp = float(clamp if clamp is not None else -1)
     padding = tuple(padding) if isinstance(padding, (tuple, list)) else (padding, padding)
-    if not _fusable(x, w, b, styles, dcoefs, noise, act):
-        return _unfused(x, w, b, styles, dcoefs, noise, stride, padding, flip_weight, act, alpha, gain, clamp if clamp >= 0 else None)
+    if not _fusable(x, w, b, styles, dcoefs, noise, act, gain):
+        return _conv_then_tail(x, w, b, styles, dcoefs, noise, stride, padding, flip_weight, act, alpha, gain, clamp if clamp >= 0 else None)
     op = _fused_op(tuple(int(s) for s in w.shape), int(stride), padding, bool(flip_weight), act, alpha, gain, clamp)
     return op.apply(x, w, b, styles, dcoefs, noise)
 
@@ -112,10 +127,19 @@ def _fused_op(weight_shape, stride, padding, flip_weight, act, alpha, gain, clam
             nbytes = (x.numel() + y.numel() + wc.numel()) * x.element_size()
             ws = _cg._attach_workspace(d, x.device)
             tc = _lib.lib().sgb_conv2d_uses_tensor_cores(d)
-            with torch.cuda.device(x.device), _lib.prof('conv_fwd_tc' if tc else 'conv_fwd_simt', flops, nbytes):
-                rc = _lib.lib().sgb_conv2d_forward(d, _lib.ptr(x), _lib.ptr(wc), _lib.ptr(y), _lib.stream_ptr(x.device))
-            _lib.check(rc, 'conv2d_forward (fused epilogue)')
-            del ws
+            if enabled == 'tma' and tc != 3:
+                # not a TMA-kernel convolution: same values from the convolution + the one-pass tail; the backward below (one
+                # pass over dy and y, then the two gradient convolutions) is the same either way
+                del ws, y
+                with torch.no_grad():
+                    y = _conv_then_tail(x, w, b, styles, dcoefs, noise, stride, padding, flip_weight, act, alpha, gain, clamp_arg)
+            else:
+                tag = (f"{str(x.dtype)[6:]} x[{n},{ci},{x.shape[2]},{x.shape[3]}] co{co} k{kh} s{stride}{' mod' if sc is not None else ''}"
+                       f"{' tma' if tc == 3 else ''} +tail") if _lib.PROFILE is not None else None
+                with torch.cuda.device(x.device), _lib.prof('conv_fwd_tc' if tc else 'conv_fwd_simt', flops, nbytes, tag):
+                    rc = _lib.lib().sgb_conv2d_forward(d, _lib.ptr(x), _lib.ptr(wc), _lib.ptr(y), _lib.stream_ptr(x.device))
+                _lib.check(rc, 'conv2d_forward (fused epilogue)')
+                del ws
             # y is only kept when the backward depends on it; like the reference (bias_act.py:152-155) a plain linear
             # epilogue does not, so callers may modify its output in place (`y.add_(x)`, discriminators.py:300)
             keep_y = act != 'linear' or clamp >= 0 or dcoefs is not None

@@ -73,21 +73,24 @@ def setup_filter(f, device=torch.device('cpu'), normalize=True, flip_filter=Fals
 
 
 separable_kernel = os.environ.get('SGB_FIR_SEP', '1') != '0'     # A/B switch: the separable strip kernel for plain FIR passes
-_sep_cache = {}     # id(filter tensor) -> (weakref to it, version, (row, col) or None)
+_sep_cache = {}     # (data_ptr, shape, strides, version) -> (the tensor, (row, col) or None)
+stats = dict(sep=0, general=0, unseen_in_capture=0)     # launches by kernel (tests)
 
 
 def _separable_taps(f2d, flip, gain):
     """(fx, fy) as 4-tap host lists in application order if the (at most 4 x 4) filter is an outer product, else None.
-    The factorisation needs the filter values on the host: one device->host copy per filter TENSOR (module buffers such as
-    `resample_filter` are long-lived), never during CUDA-graph capture (an unseen filter then takes the general kernel)."""
+    The factorisation needs the filter values on the host: one device->host copy per filter BUFFER (keyed by address and
+    version counter -- autograd hands the backward a new Python object for the saved filter, so identity of the object is
+    not enough; the entry keeps the tensor alive, so the address cannot be recycled), never during CUDA-graph capture (an
+    unseen filter then takes the general kernel)."""
     fh, fw = f2d.shape
     if fh > 4 or fw > 4:
         return None
-    hit = _sep_cache.get(id(f2d))
-    if hit is not None and (hit[0]() is not f2d or hit[1] != f2d._version):
-        hit = None
+    key = (f2d.data_ptr(), fh, fw, f2d.stride(0), f2d.stride(1), f2d._version)
+    hit = _sep_cache.get(key)
     if hit is None:
         if torch.cuda.is_current_stream_capturing():
+            stats['unseen_in_capture'] += 1
             return None
         a = f2d.detach().to('cpu', torch.float64).numpy()
         fac = None
@@ -96,8 +99,9 @@ def _separable_taps(f2d, flip, gain):
             row, col = a[r0, :].copy(), a[:, c0] / a[r0, c0]
             if np.abs(np.outer(col, row) - a).max() <= 1e-7 * np.abs(a[r0, c0]):
                 fac = (row, col)
-        key = id(f2d)
-        hit = (weakref.ref(f2d, lambda _r, k=key: _sep_cache.pop(k, None)), f2d._version, fac)
+        if len(_sep_cache) > 256:
+            _sep_cache.clear()
+        hit = (f2d.detach(), f2d._version, fac)
         _sep_cache[key] = hit
     if hit[2] is None:
         return None
@@ -131,6 +135,7 @@ def _run(x, f2d, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain)
                 rc = _lib.lib().sgb_upfirdn2d_sep(_lib.ptr(x), fx, fy, _lib.ptr(y), _lib.dtype_code(x), n, c, ih, iw, _lib.strides4(x),
                                                   oh, ow, _lib.strides4(y), padx0, pady0, _lib.stream_ptr(x.device))
             _lib.check(rc, 'upfirdn2d_sep')
+            stats['sep'] += 1
             return y
     with torch.cuda.device(x.device), _lib.prof('upfirdn2d', 0.0, (x.numel() + y.numel()) * x.element_size()):
         rc = _lib.lib().sgb_upfirdn2d(_lib.ptr(x), _lib.ptr(f2d), _lib.ptr(y), _lib.dtype_code(x),
@@ -139,6 +144,7 @@ def _run(x, f2d, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain)
                                       upx, upy, downx, downy, padx0, pady0, int(bool(flip)), float(gain),
                                       _lib.stream_ptr(x.device))
     _lib.check(rc, 'upfirdn2d')
+    stats['general'] += 1
     return y
 
 

@@ -360,7 +360,8 @@ class Trainer:
         with torch.no_grad():
             for m, sd in zip(mods, snap['mods']):
                 for k, v in m.state_dict().items():
-                    v.copy_(sd[k])
+                    if not torch.equal(v, sd[k]):      # untouched tensors (FIR filters, noise_const) keep their version counter:
+                        v.copy_(sd[k])                 # ops cache host-side facts about constant buffers by (address, version)
             for o, sd in zip(opts, snap['opts']):
                 if sd['state']:
                     o.load_state_dict(sd)
