@@ -79,11 +79,12 @@ def worker(backend):
 def config_a(H, backend):
     """BASELINE configs[0] at its real size (sg2ada.yaml: 64x64, batch 8, 512 channels, D 'orig'): gradients of Gmain / Dmain /
     Dreg from the unchanged callers on the GPU against the SAME reference modules run on the CPU in fp32 (impl='ref').  The
-    'reference' worker runs first, computes that CPU golden and leaves it in gpurun_out/ for the 'sgb200' worker (whose ops
-    refuse CPU tensors)."""
+    'reference' worker runs first, computes that CPU golden and leaves it in the system temp directory for the 'sgb200' worker
+    (whose ops refuse CPU tensors).  ~600 MB in fp64: it must NOT sit in gpurun_out/, whose size is capped at 64 MiB."""
     import numpy as np
     import torch
-    path = os.path.join(ROOT, 'gpurun_out', 'parity_config_a_golden.npz')
+    import tempfile
+    path = os.path.join(tempfile.gettempdir(), 'sgb200_parity_config_a_golden.npz')
     g = torch.Generator().manual_seed(5)
     zz = torch.randn(8, 512, generator=g)
     real = torch.rand(8, 3, 64, 64, generator=g) * 2 - 1

@@ -36,6 +36,29 @@ _ACT_ID = {'linear': 1, 'lrelu': 3}
 enabled = os.environ.get('SGB_FUSED_CONV', '0')
 if enabled in ('0', '1'):
     enabled = enabled == '1'
+# SGB_FUSED_CONV_MAIN ('0' | 'tma' | '1'): the same switch, but only for phases whose backward is first order (Gmain / Dmain);
+# the training harness sets `enabled` from it per phase.  Under create_graph=True (Greg / Dreg) the fused forward is a loss
+# whatever the kernel costs: its differentiable backward re-evaluates the convolution (the un-fused tail re-evaluates only
+# itself, from the saved convolution output).
+main_phase_mode = os.environ.get('SGB_FUSED_CONV_MAIN', '0')
+if main_phase_mode in ('0', '1'):
+    main_phase_mode = main_phase_mode == '1'
+
+
+class phase_mode:
+    """with fused_conv.phase_mode(first_order=True|False): ... -- applies `main_phase_mode` for the duration of a training phase"""
+    def __init__(self, first_order):
+        self.first_order = first_order
+
+    def __enter__(self):
+        global enabled
+        self.old = enabled
+        if main_phase_mode:
+            enabled = main_phase_mode if self.first_order else False
+
+    def __exit__(self, *a):
+        global enabled
+        enabled = self.old
 
 
 def _noise4(noise, n, h, w):

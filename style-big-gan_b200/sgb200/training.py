@@ -25,6 +25,7 @@ import torch.distributed as dist
 
 from . import networks
 from .ops import conv2d_gradfix
+from .ops import fused_conv
 
 
 @dataclass
@@ -303,14 +304,15 @@ class Trainer:
         module.requires_grad_(True)
         gain = ph['interval']
         name = ph['name']
-        if name == 'Gmain':
-            val = self.phase_Gmain(z, gain)
-        elif name == 'Greg':
-            val = self.phase_Greg(z, gain, pl_noise=self.static_pl_noise)
-        elif name == 'Dmain':
-            val = self.phase_Dmain(z, real, gain)
-        else:
-            val = self.phase_Dreg(real, gain)
+        with fused_conv.phase_mode(first_order=name in ('Gmain', 'Dmain')):
+            if name == 'Gmain':
+                val = self.phase_Gmain(z, gain)
+            elif name == 'Greg':
+                val = self.phase_Greg(z, gain, pl_noise=self.static_pl_noise)
+            elif name == 'Dmain':
+                val = self.phase_Dmain(z, real, gain)
+            else:
+                val = self.phase_Dreg(real, gain)
         module.requires_grad_(False)
         if flat is not None:
             flat.gather()
