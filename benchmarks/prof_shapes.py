@@ -200,6 +200,30 @@ def main():
         x = cl(torch.randn(32, 64, 128, 128, device=DEV))
         return (lambda: upfirdn2d.upsample2d(x, f)), 0, 5 * x.numel() * 4
 
+    # the 512-channel layers of config-f at 4 images per GPU (fp32, 4^2 ... 64^2): a handful of tiles, latency-bound
+    def small_case(name, n, res, stride=1, transposed=False):
+        @case(name)
+        def _():
+            if transposed:
+                x = cl(torch.randn(n, 512, res, res, device=DEV))
+                w = torch.randn(512, 512, 3, 3, device=DEV) / math.sqrt(9 * 512)
+                oh = (res - 1) * stride + 3 - (2 if stride == 1 else 0)
+                fn = (lambda: conv2d_gradfix.conv_transpose2d(x, w, stride=stride, padding=(1 if stride == 1 else 0)))
+                return fn, 2.0 * n * res * res * 512 * 512 * 9, (x.numel() + n * 512 * oh * oh) * 4
+            xin = res * stride + (1 if stride == 2 else 0)
+            x = cl(torch.randn(n, 512, xin, xin, device=DEV))
+            w = torch.randn(512, 512, 3, 3, device=DEV) / math.sqrt(9 * 512)
+            fn = (lambda: conv2d_gradfix.conv2d(x, w, stride=stride, padding=(1 if stride == 1 else 0)))
+            return fn, 2.0 * n * res * res * 512 * 512 * 9, (x.numel() + n * 512 * res * res) * 4
+    for n_ in (4, 32):
+        small_case(f'small_s1_8_n{n_}', n_, 8)
+        small_case(f'small_s1_16_n{n_}', n_, 16)
+        small_case(f'small_s1_32_n{n_}', n_, 32)
+        small_case(f'small_s2_8_n{n_}', n_, 8, stride=2)          # x[n,512,17,17] -> 8 x 8
+        small_case(f'small_s2_16_n{n_}', n_, 16, stride=2)
+        small_case(f'small_T1_16_n{n_}', n_, 16, transposed=True)
+        small_case(f'small_T2_8_n{n_}', n_, 8, stride=2, transposed=True)     # 8 x 8 -> 17 x 17
+
     names = list(cases) if args.cases == 'all' else args.cases.split(',')
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
     for name in names:

@@ -26,6 +26,8 @@
 namespace sgb {
 
 int conv_wgrad_tf32(const sgb_conv_desc* d, const void* x, const void* dy, float* dw, cudaStream_t s);   // conv_wgrad_tf32.cu
+bool conv_wgrad_kys_eligible(const sgb_conv_desc* d);                                                   // conv_wgrad_kys.cu
+int conv_wgrad_kys(const sgb_conv_desc* d, const void* x, const void* dy, float* dw, cudaStream_t s);
 
 constexpr int WG_THREADS = 160;
 constexpr int WG_LOOKAHEAD = 1;          // tiles in flight per producer thread beyond the one being published
@@ -667,6 +669,8 @@ int conv_wgrad_halo(const sgb_conv_desc* d, const void* x, const void* dy, void*
   cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * wnum, s);
   SGB_REQUIRE(e == cudaSuccess, "memset failed");
   if ((int64_t)d->n * d->out_h * d->out_w == 0) return 0;
+  // few-channel 3 x 3 stride-1 layers in 16-bit types: all nine taps from one staging (filter rows stacked in M)
+  if (conv_wgrad_kys_eligible(d)) return conv_wgrad_kys(d, x, dy, (float*)dw, s);
   if (d->dtype == SGB_F16) return dispatch_wgrad_halo<__half, 0>(d, x, dy, (float*)dw, s);
   if (d->dtype == SGB_BF16) return dispatch_wgrad_halo<__nv_bfloat16, 1>(d, x, dy, (float*)dw, s);
   // fp32: kind::tf32 takes MN-major operands only in the SWIZZLE_128B_BASE32B layout (conv_wgrad_tf32.cu); the earlier

@@ -131,6 +131,9 @@ def test_umma_gradients_fp16():
     (2, 160, 32, 12, 3, 1, 1),        # two c tiles with a tail (160 = 128 + 32)
     (2, 64, 128, 16, 1, 1, 0),        # 1x1 (D skip)
     (70, 32, 32, 8, 3, 1, 1),         # more tiles than CTAs want: several tiles per CTA, pipeline wrap-around
+    (2, 64, 32, 24, 3, 1, 1),         # one dy block (co = 32): filter rows stacked in M, 24 rows = 1.5 tiles of 16
+    (1, 48, 64, 70, 3, 1, 0),         # no padding (out = in - 2), partial column tile, ci tail; many row tiles
+    (5, 64, 64, 128, 3, 1, 1),        # a real layer size: 128 x 128, every CTA walks many tiles
 ])
 def test_umma_wgrad_vs_oracle(dtype, case):
     from sgb200.ops import conv2d_gradfix as cg
