@@ -33,13 +33,24 @@ import torch.distributed as dist  # noqa: E402
 
 
 def load_peaks():
+    """HBM and bf16 tensor peaks: MEASURED_PEAKS.json (driver-written).  The convolutions of the headline workload run on
+    kind::tf32 MMAs, for which that file has no number: profiles/r2_tensor_peaks.json holds the TF32 / fp16 rates measured on this
+    pool's B200 the same way (benchmarks/measure_peaks.py: cuBLAS 8192^3, burst and sustained)."""
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
         with open(path) as f:
             p = json.load(f)
-        return dict(hbm=p['hbm_gbs'], tc_burst=p['bf16_tflops'], tc_sustained=p.get('bf16_tflops_sustained', p['bf16_tflops']),
-                    source='measured (MEASURED_PEAKS.json)')
-    return dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, source='fallback (B200_PROFILING.md)')
+        out = dict(hbm=p['hbm_gbs'], tc_burst=p['bf16_tflops'], tc_sustained=p.get('bf16_tflops_sustained', p['bf16_tflops']),
+                   source='measured (MEASURED_PEAKS.json)')
+    else:
+        out = dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, source='fallback (B200_PROFILING.md)')
+    tpath = os.path.join(ROOT, 'profiles', 'r2_tensor_peaks.json')
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            t = json.load(f)
+        out['tf32_sustained'] = t['tf32']['sustained_tflops']
+        out['fp16_sustained'] = t['fp16']['sustained_tflops']
+    return out
 
 
 class ClockSampler:
@@ -374,13 +385,18 @@ def roofline_of(summ, cfg, workload, fp32_mode, peaks, steps):
     (tcgen05 K = 8 per instruction instead of 16), so fp32 tensors are reported against bf16 sustained / 2.  Mixed workloads
     (f1024: fp32 below 128^2, fp16 above) are reported against the fp16 rate, the stricter denominator."""
     traffic = {}
-    tpath = os.path.join(ROOT, 'profiles', 'r1_conv_traffic.json')        # DRAM bytes per launch from ncu (profiles/README.md)
+    tpath = os.path.join(ROOT, 'profiles', 'r2_conv_traffic.json')        # DRAM bytes per launch from ncu (profiles/README.md)
     if os.path.exists(tpath) and workload == 'ffhq256':
         with open(tpath) as f:
             traffic = json.load(f)
     total_ms = sum(d['ms'] for d in summ.values()) or 1.0
     tf32 = cfg.num_fp16_res == 0 and fp32_mode == 'tf32'
-    tc_peak = peaks['tc_sustained'] / (2 if tf32 else 1)
+    if tf32 and 'tf32_sustained' in peaks:
+        tc_peak, tc_src = peaks['tf32_sustained'], 'measured cuBLAS TF32 8192^3 sustained (profiles/r2_tensor_peaks.json, benchmarks/measure_peaks.py)'
+    elif tf32:
+        tc_peak, tc_src = peaks['tc_sustained'] / 2, peaks['source'] + ' bf16 sustained / 2 (TF32 MMA rate)'
+    else:
+        tc_peak, tc_src = peaks['tc_sustained'], peaks['source'] + ' bf16 sustained (= fp16 MMA rate)'
     fam = {}
     for k, d in summ.items():
         e = dict(ms_per_step=d['ms'] / steps, launches_per_step=d['launches'] / steps)
@@ -397,7 +413,7 @@ def roofline_of(summ, cfg, workload, fp32_mode, peaks, steps):
         ach = d['flops'] / (d['ms'] / 1000.0) / 1e12
         roof = dict(kernel=dom, bound='tensor', achieved=ach, peak=tc_peak, unit='TFLOP/s', frac=ach / tc_peak,
                     traffic=(traffic.get(dom) or {}).get('dram_bytes_per_launch'),
-                    peak_source=peaks['source'] + (' bf16 sustained / 2 (TF32 MMA rate)' if tf32 else ' bf16 sustained (= fp16 MMA rate)'),
+                    peak_source=tc_src,
                     launches=d['launches'], avg_launch_ms=d['ms'] / d['launches'], share_of_kernel_time=d['ms'] / total_ms,
                     algorithmic_flops_per_launch=d['flops'] / d['launches'],
                     hbm_view=dict(gbs=d['bytes'] / (d['ms'] / 1000.0) / 1e9, frac=d['bytes'] / (d['ms'] / 1000.0) / 1e9 / peaks['hbm']))

@@ -54,7 +54,12 @@ def launches(src, dst):
 
 
 def full(src, dst):
-    out = subprocess.run(['ncu', '-i', src, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    # src: an .ncu-rep, or the `ncu -i rep --page raw --csv` export made on the GPU box (the reports themselves are too large
+    # to bring back: gpurun_out/ is capped at 64 MiB)
+    if src.endswith('.csv'):
+        out = open(src).read()
+    else:
+        out = subprocess.run(['ncu', '-i', src, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     idx = [(m, hdr.index(m)) for m in FULL_METRICS if m in hdr]

@@ -162,6 +162,17 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(HaloParams p
     uint32_t ph_i = 0;                                 // phase of the issue position
     int pub_tile_cb = 0;                               // channel block of patch `pub` within its tile
     int64_t pub_tile = blockIdx.x;                     // tile of patch `pub`
+    // image / virtual row of that tile's first patch row, refreshed once per tile (the 64-bit divisions of decode_tile were
+    // ~15 % of the producers' samples when they ran once per K block: profiles/README.md, small 512-channel layers)
+    int pub_n0 = 0, pub_rem0 = 0;
+    auto pub_decode = [&]() {
+      if (pub_tile < p.total_tiles) {
+        int nt_, u0o, x0_;
+        decode_tile(p, GT, pub_tile, nt_, u0o, x0_);
+        pub_n0 = u0o / p.VR; pub_rem0 = u0o - pub_n0 * p.VR;
+      }
+    };
+    pub_decode();
 
     auto publish = [&]() {                             // the oldest unpublished patch has landed: scaling, fence, arrive
       const int sa = sa_p;
@@ -172,11 +183,9 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(HaloParams p
       // TF32 (cvt.rna, what cuDNN's TF32 convolutions amount to) in the same in-place pass that applies the style scale.
       if (scb || (KIND == 2 && !(p.debug & 64))) {        // SGB_HALO_DEBUG=64: A/B switch, leave the truncation to the MMA
         uint8_t* dst = a_base + sa * p.a_stage_bytes;
-        int nt_, u0o, x0_;
-        decode_tile(p, GT, pub_tile, nt_, u0o, x0_);
         const int co = pub_tile_cb * BK + j * TC;
         if (co < d.ci) {
-          const int n0 = u0o / p.VR, rem0 = u0o - n0 * p.VR;
+          const int n0 = pub_n0, rem0 = pub_rem0;
 #pragma unroll
           for (int i = 0; i < MAX_SLOTS; i++) {
             if (hrc[i] >= 0) {
@@ -212,7 +221,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(HaloParams p
       __syncwarp();                                    // one mbarrier arrival per warp instead of per thread
       if (lane == 0) mbar_arrive(smem_u32(&a_full[sa]));
       pub++;
-      if (++pub_tile_cb == p.cblocks) { pub_tile_cb = 0; pub_tile += gridDim.x; }
+      if (++pub_tile_cb == p.cblocks) { pub_tile_cb = 0; pub_tile += gridDim.x; pub_decode(); }
     };
 
     for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {

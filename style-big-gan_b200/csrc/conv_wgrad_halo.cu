@@ -111,19 +111,28 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_halo_kernel(WgradHal
     const int tiles_per_img = p.row_tiles * p.col_tiles;
     int pub = 0;
 
-    auto tile_origin = [&](int i, int& n, int& oy0, int& ox0) {
-      const int64_t tt = t_begin + i;
-      n = (int)(tt / tiles_per_img);
-      const int rem = (int)(tt - (int64_t)n * tiles_per_img);
+    // tile coordinates advance incrementally: one cursor for the loads, one for publishing (the 64-bit division of a
+    // per-tile decode was a dependent ~1 K cycle chain in every producer thread, once per pipeline step)
+    struct Cursor { int n, oy0, ox0; };
+    auto cursor_at = [&](int64_t tt) {
+      Cursor c;
+      c.n = (int)(tt / tiles_per_img);
+      const int rem = (int)(tt - (int64_t)c.n * tiles_per_img);
       const int tr = rem / p.col_tiles;
-      oy0 = tr * p.TH; ox0 = (rem - tr * p.col_tiles) * 8;
+      c.oy0 = tr * p.TH; c.ox0 = (rem - tr * p.col_tiles) * 8;
+      return c;
     };
+    auto advance = [&](Cursor& c) {
+      c.ox0 += 8;
+      if (c.ox0 >= p.col_tiles * 8) { c.ox0 = 0; c.oy0 += p.TH; if (c.oy0 >= p.row_tiles * p.TH) { c.oy0 = 0; c.n++; } }
+    };
+    Cursor cur_i = cursor_at(t_begin), cur_p = cur_i;
 
     auto publish = [&](int i) {
       const int sa = i % SA;
+      const int n = cur_p.n;
+      advance(cur_p);
       if (scb && jb < cpb) {                                        // in-place style scaling of the chunks this thread copied
-        int n, oy0, ox0;
-        tile_origin(i, n, oy0, ox0);
         const float* sp = scb + (int64_t)n * d.ci + c0 + jb * TC;
         float sv[TC];
 #pragma unroll
@@ -149,8 +158,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_halo_kernel(WgradHal
         }
       }
       if (sca && ja < cpa) {                                        // same for the dy tile (out_scale)
-        int n, oy0, ox0;
-        tile_origin(i, n, oy0, ox0);
         const float* sp = sca + (int64_t)n * d.co + o0 + ja * TC;
         float sv[TC];
 #pragma unroll
@@ -180,8 +187,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_halo_kernel(WgradHal
     uint32_t ph_i = 0;
     for (int i = 0; i < ntiles; i++) {
       const int sa = sa_i;
-      int n, oy0, ox0;
-      tile_origin(i, n, oy0, ox0);
+      const int n = cur_i.n, oy0 = cur_i.oy0, ox0 = cur_i.ox0;
+      advance(cur_i);
       mbar_wait(smem_u32(&empty_bar[sa]), ph_i ^ 1);
       if (++sa_i == SA) { sa_i = 0; ph_i ^= 1; }
       const uint32_t a_dst = smem_u32(smem + sa * p.stage_bytes);
