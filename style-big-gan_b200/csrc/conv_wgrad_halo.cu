@@ -48,6 +48,7 @@ struct WgradHaloParams {
   int a_plane, b_plane;       // bytes between channel chunks
   int a_bytes, stage_bytes;
   int stages;
+  int lookahead;              // halo kernel: tiles in flight per producer thread beyond the one being published
   int nstg;                   // fp32 split kernel: staging buffers (tiles in flight from L2 / HBM = nstg - 1)
 };
 
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_halo_kernel(WgradHal
   constexpr int TC = 16 / sizeof(T);
   constexpr int KPM = 32 / (int)sizeof(T);           // pixels per MMA (K = 32 bytes)
   constexpr uint32_t IDESC = make_idesc(KIND, BNC, 1);
-  constexpr int MAX_STAGES = 4;
+  constexpr int MAX_STAGES = 8;
 
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], accum_bar;
@@ -221,8 +222,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_halo_kernel(WgradHal
         }
       }
       cp_async_commit();
-      if (i - pub >= WG_LOOKAHEAD) {
-        cp_async_wait<WG_LOOKAHEAD>();
+      if (i - pub >= p.lookahead) {
+        cp_async_wait_n(p.lookahead);
         publish(pub++);
       }
     }
@@ -594,11 +595,16 @@ static int launch_wgrad_halo(const sgb_conv_desc* d, const void* x, const void* 
     p.a_plane = npa * 16; p.b_plane = npb * 16;
     p.a_bytes = (UM / TC) * p.a_plane;
     p.stage_bytes = (p.a_bytes + (BNC / TC) * p.b_plane + 127) / 128 * 128;
-    stages = budget / p.stage_bytes; if (stages > 4) stages = 4;
+    stages = budget / p.stage_bytes; if (stages > 8) stages = 8;
     if (stages >= 3 || TH == 4) break;
   }
   SGB_REQUIRE(stages >= 2, "wgrad halo: tile does not fit shared memory");
   p.TH = TH; p.stages = stages;
+  // tiles in flight per producer thread beyond the one being published (SGB_WGRAD_LA overrides); up to 8 stages
+  static const int env_la = [] { const char* e = getenv("SGB_WGRAD_LA"); return e ? atoi(e) : 0; }();
+  p.lookahead = 1;        // measured (r2_run28.sh, config-f step): 1 tile ahead 52.2 ms, stages - 2 ahead 53.0 ms
+  if (env_la > 0 && env_la < stages) p.lookahead = env_la;
+  if (p.lookahead > 6) p.lookahead = 6;
   p.row_tiles = (d->out_h + TH - 1) / TH; p.col_tiles = (d->out_w + 7) / 8;
   p.total_tiles = (int64_t)d->n * p.row_tiles * p.col_tiles;
   const int64_t base = (int64_t)otiles * p.ctiles * d->kh;
