@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(HaloParams p
                   if (has_act) {
                     if (d.bias) v += to_acc<T>(((const T*)d.bias)[o]);
                     v = (v > 0.f ? v : v * alpha) * gain;
-                    if (clamp >= 0.f) v = fminf(fmaxf(v, -clamp), clamp);
+                    if (clamp >= 0.f) v = v < -clamp ? -clamp : (v > clamp ? clamp : v);      // explicit compares: NaN propagates like torch.clamp
                   }
                 }
                 val[e] = v;

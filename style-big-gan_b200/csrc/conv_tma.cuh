@@ -1,5 +1,8 @@
 // tcgen05 implicit-GEMM convolution with TMA-staged activation patches (stride 1, kernels up to 3x3, channels_last):
-// forward of conv2d AND of conv_transpose2d stride 1 (= the data gradient of the other one).
+// forward of conv2d AND of conv_transpose2d stride 1 (= the data gradient of the other one).  S2 = 1: the 3 x 3 stride-2
+// convolution through a tensor map with element stride 2 along W (two boxes per K block: the even- and the odd-column plane of the
+// patch; a tap moves the descriptor's start inside its plane, consecutive output rows are two patch rows apart) -- exact, opt-in
+// (conv_tma.cu: measured no faster than conv_halo_kernel's MODE 1).
 //
 // conv_halo_kernel stages the input patch of a super-tile with 8 producer warps (cp.async, 16 bytes per instruction, the
 // source address of every chunk computed in registers).  The ncu captures of round 2 (profiles/README.md) show those
@@ -39,7 +42,9 @@ constexpr int TMA_TILE_H = 16, TMA_TILE_W = 8;
 struct TmaConvParams {
   sgb_conv_desc d;
   const void* wpack; void* y;
-  int HR, HC;               // patch rows / columns
+  int HR, HC;               // patch rows / columns (stride 2: columns of ONE column-parity plane)
+  int plane_bytes;          // stride 2: bytes between the even-column and the odd-column plane of a stage (multiple of 1024)
+  int sbo_bytes;            // bytes between consecutive output rows of the tile in the patch (one patch row, two for stride 2)
   int top, left;            // patch origin relative to the tile origin (input coordinates)
   int row_tiles, col_tiles, ntiles;
   int64_t total_tiles;
@@ -70,8 +75,9 @@ __device__ __forceinline__ void tma_decode_tile(const TmaConvParams& p, int gt, 
   n = (int)(mt / p.row_tiles);
 }
 
-template <class T, int KIND, int BN, int KB, int GT>
+template <class T, int KIND, int BN, int KB, int GT, int S2>
 __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_constant__ CUtensorMap tmx, TmaConvParams p) {
+  constexpr int NPL = S2 ? 2 : 1;                      // column-parity planes per stage
   constexpr int TC = 16 / sizeof(T);
   constexpr int CH = KB / 16;                          // 16-byte chunks of K per stage
   constexpr int KSTEPS = KB / 32;                      // MMAs per tap per tile (32 bytes of K each)
@@ -127,7 +133,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_c
       asm volatile("prefetch.tensormap [%0];" :: "l"(&tmx) : "memory");
       int sa = 0;
       uint32_t ph = 0;
-      const uint32_t bytes = (uint32_t)(p.HR * p.HC * KB);
+      const uint32_t bytes = (uint32_t)(NPL * p.HR * p.HC * KB);
       for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int ntile, n, oy0, ox0;
         tma_decode_tile(p, GT, tile, ntile, n, oy0, ox0);
@@ -135,7 +141,16 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_c
           mbar_wait(smem_u32(&a_empty[sa]), ph ^ 1);
           const uint32_t bar = smem_u32(&a_full[sa]);
           mbar_arrive_expect_tx(bar, bytes);
-          tma_load_4d(smem_u32(a_base + sa * p.a_stage_bytes), &tmx, cb * (KB / (int)sizeof(T)), ox0 - p.left, oy0 - p.top, n, bar);
+          if (S2) {
+            // stride 2: the tensor map walks the columns with element stride 2, so one box is the even-column (q = 0) or
+            // the odd-column (q = 1) plane of the patch: 8 consecutive outputs of a row are again consecutive pixels
+            const uint32_t dst = smem_u32(a_base + sa * p.a_stage_bytes);
+#pragma unroll
+            for (int q = 0; q < 2; q++)
+              tma_load_4d(dst + q * p.plane_bytes, &tmx, cb * (KB / (int)sizeof(T)), 2 * ox0 - p.left + q, 2 * oy0 - p.top, n, bar);
+          } else {
+            tma_load_4d(smem_u32(a_base + sa * p.a_stage_bytes), &tmx, cb * (KB / (int)sizeof(T)), ox0 - p.left, oy0 - p.top, n, bar);
+          }
           if (++sa == SA) { sa = 0; ph ^= 1; }
         }
       }
@@ -154,7 +169,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_c
         tma_decode_tile(p, GT, tile, ntile, n, oy0, ox0);
         for (int cb = 0; cb < p.cblocks; cb++) {
           mbar_wait(smem_u32(&a_full[sa]), ph);
-          uint8_t* st = a_base + sa * p.a_stage_bytes;
+          for (int pl = 0; pl < NPL; pl++) {
+          uint8_t* st = a_base + sa * p.a_stage_bytes + pl * p.plane_bytes;
           const uint32_t st_addr = smem_u32(st);
           for (int q = t; q < nchunks; q += 128) {
             const int pix = q / CH, pc = q - pix * CH;                 // physical chunk position within the row
@@ -182,6 +198,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_c
               *ptr = v;
             }
           }
+          }
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&a_ready[sa]));
@@ -191,7 +208,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) conv_tma_kernel(const __grid_c
     }
   } else if (warp == 4) {
     // =========================== MMA issuer ===========================
-    const uint32_t sbo = (uint32_t)(p.HC * KB);
+    const uint32_t sbo = (uint32_t)p.sbo_bytes;
     const uint32_t a_hi0 = smem_desc_hi(sbo) | (A_LAYOUT << 29), b_hi = smem_desc_hi(128);
     const uint32_t b_lo_base = smem_desc_lo(smem_u32(b_base), BN * 16);
     const uint32_t b_stage_u = (uint32_t)(p.tps * B_TAP_BYTES) >> 4;
@@ -415,16 +432,23 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 PFN_encodeTiled tma_encode_fn();      // conv_tma.cu: cuTensorMapEncodeTiled through cudaGetDriverEntryPoint (no -lcuda)
 
-template <class T, int KIND, int BN, int KB, int GT>
+template <class T, int KIND, int BN, int KB, int GT, int S2>
 int launch_tma(const sgb_conv_desc* d, const void* x, const void* w, void* y, cudaStream_t s) {
   constexpr int TC = 16 / sizeof(T);
   constexpr int SLAB = (BN * (int)sizeof(T) >= 128) ? 128 / (int)sizeof(T) : BN;
   constexpr int PITCH = SLAB * (int)sizeof(T) + 16;
   TmaConvParams p; p.d = *d; p.y = y; p.wpack = d->workspace;
   const int TW = TMA_TILE_W * GT;
-  p.HR = TMA_TILE_H + d->kh - 1; p.HC = TW + d->kw - 1;
-  p.top = d->transposed ? (d->kh - 1 - d->pad_y) : d->pad_y;
-  p.left = d->transposed ? (d->kw - 1 - d->pad_x) : d->pad_x;
+  if (S2) {
+    p.HR = 2 * (TMA_TILE_H - 1) + d->kh; p.HC = TW + (d->kw - 1 + 1) / 2;      // rows: all of them; columns: one parity plane
+    p.top = d->pad_y; p.left = d->pad_x;
+  } else {
+    p.HR = TMA_TILE_H + d->kh - 1; p.HC = TW + d->kw - 1;
+    p.top = d->transposed ? (d->kh - 1 - d->pad_y) : d->pad_y;
+    p.left = d->transposed ? (d->kw - 1 - d->pad_x) : d->pad_x;
+  }
+  p.plane_bytes = (p.HR * p.HC * KB + 1023) / 1024 * 1024;
+  p.sbo_bytes = (S2 ? 2 : 1) * p.HC * KB;
   p.row_tiles = (d->out_h + TMA_TILE_H - 1) / TMA_TILE_H;
   p.col_tiles = (d->out_w + TW - 1) / TW;
   p.ntiles = (d->co + BN - 1) / BN;
@@ -434,9 +458,9 @@ int launch_tma(const sgb_conv_desc* d, const void* x, const void* w, void* y, cu
   for (int tap = 0; tap < p.taps; tap++) {
     const int ky = tap / d->kw, kx = tap - ky * d->kw;
     const int pr = d->transposed ? (d->kh - 1 - ky) : ky, pc = d->transposed ? (d->kw - 1 - kx) : kx;
-    p.tap_aoff[tap] = pr * p.HC + pc;
+    p.tap_aoff[tap] = S2 ? ((kx & 1) * (p.plane_bytes / KB) + ky * p.HC + (kx >> 1)) : (pr * p.HC + pc);
   }
-  p.a_stage_bytes = (p.HR * p.HC * KB + 1023) / 1024 * 1024;
+  p.a_stage_bytes = (S2 ? 2 : 1) * p.plane_bytes;
   const bool y_al = aligned16(y) && d->y_strides[0] % TC == 0 && d->y_strides[2] % TC == 0 && d->y_strides[3] % TC == 0;
   p.vec_store = (d->co % TC == 0 && y_al) ? 1 : 0;
   static const int no_round = [] { const char* e = getenv("SGB_TMA_NOROUND"); return e ? atoi(e) : 0; }();
@@ -447,12 +471,16 @@ int launch_tma(const sgb_conv_desc* d, const void* x, const void* w, void* y, cu
   SGB_REQUIRE(d->act == 0 || d->act == SGB_ACT_LINEAR || d->act == SGB_ACT_LRELU, "fused epilogue supports linear and lrelu only");
   if (d->act == SGB_ACT_LINEAR) p.d.alpha = 1.f;
 
+  // weights first: the pack kernel's launch also binds this thread to the device's primary context, which the driver entry
+  // point below needs (an autograd worker thread whose first CUDA call was cuTensorMapEncodeTiled got CUDA_ERROR_INVALID_CONTEXT)
+  if (int r = pack_weights_umma(d, w, BN, s)) return r;
   // tensor map of x: dims (innermost first) {C, W, H, N}, byte strides of W, H, N; box {KB bytes of channels, HC, HR, 1}
   CUtensorMap tm;
   const cuuint64_t gdim[4] = {(cuuint64_t)d->ci, (cuuint64_t)d->in_w, (cuuint64_t)d->in_h, (cuuint64_t)d->n};
   const cuuint64_t gstr[3] = {(cuuint64_t)d->x_strides[3] * sizeof(T), (cuuint64_t)d->x_strides[2] * sizeof(T), (cuuint64_t)d->x_strides[0] * sizeof(T)};
-  const cuuint32_t box[4] = {(cuuint32_t)(KB / sizeof(T)), (cuuint32_t)p.HC, (cuuint32_t)p.HR, 1u};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  // element stride 2 along W (stride-2 convolution): TMA loads ceil(box / stride) elements, so a plane of HC columns is a box of 2 * HC
+  const cuuint32_t box[4] = {(cuuint32_t)(KB / sizeof(T)), (cuuint32_t)((S2 ? 2 : 1) * p.HC), (cuuint32_t)p.HR, 1u};
+  const cuuint32_t estr[4] = {1, (cuuint32_t)(S2 ? 2 : 1), 1, 1};
   const CUtensorMapDataType dt = KIND == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (KIND == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
   PFN_encodeTiled enc = tma_encode_fn();
   SGB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
@@ -461,7 +489,6 @@ int launch_tma(const sgb_conv_desc* d, const void* x, const void* w, void* y, cu
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SGB_REQUIRE(cr == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (" + std::to_string((int)cr) + ")");
 
-  if (int r = pack_weights_umma(d, w, BN, s)) return r;
   const int budget = 223 * 1024;                    // 226 KB of dynamic shared memory - 1 KB alignment slack - margin
   const int stg_bytes = 4 * 32 * PITCH + 4 * 2 * BN * (int)sizeof(float);      // store slabs + per-warp scale / bias vectors
   const int b_tap = BN * KB;
@@ -500,7 +527,7 @@ int launch_tma(const sgb_conv_desc* d, const void* x, const void* w, void* y, cu
   p.stg_off = sa * p.a_stage_bytes + sb * b_stage;
   }
   const size_t smem = (size_t)p.stg_off + stg_bytes + 2048;
-  auto kern = conv_tma_kernel<T, KIND, BN, KB, GT>;
+  auto kern = conv_tma_kernel<T, KIND, BN, KB, GT, S2>;
   SGB_REQUIRE(smem <= 226 * 1024, "shared memory plan exceeds 226 KB");
   SGB_SET_MAX_SMEM(kern, 226 * 1024);
   const int64_t grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
@@ -512,10 +539,11 @@ int launch_tma(const sgb_conv_desc* d, const void* x, const void* w, void* y, cu
 // (BN, KB, GT) -> launcher
 template <class T, int KIND>
 int dispatch_tma(int bn, int kb, int gt, const sgb_conv_desc* d, const void* x, const void* w, void* y, cudaStream_t s) {
-#define SGB_TMA_CASE(BN_, KB_, GT_) \
-  if (bn == BN_ && kb == KB_ && gt == GT_) return launch_tma<T, KIND, BN_, KB_, GT_>(d, x, w, y, s);
-  SGB_TMA_CASE(32, 64, 4) SGB_TMA_CASE(64, 64, 4)
-  SGB_TMA_CASE(32, 128, 2) SGB_TMA_CASE(64, 128, 2) SGB_TMA_CASE(128, 128, 2) SGB_TMA_CASE(256, 128, 2)
+#define SGB_TMA_CASE(BN_, KB_, GT_, S2_) \
+  if (bn == BN_ && kb == KB_ && gt == GT_ && (d->stride == 2) == (S2_ == 1)) return launch_tma<T, KIND, BN_, KB_, GT_, S2_>(d, x, w, y, s);
+  SGB_TMA_CASE(32, 64, 4, 0) SGB_TMA_CASE(64, 64, 4, 0)
+  SGB_TMA_CASE(32, 128, 2, 0) SGB_TMA_CASE(64, 128, 2, 0) SGB_TMA_CASE(128, 128, 2, 0) SGB_TMA_CASE(256, 128, 2, 0)
+  SGB_TMA_CASE(32, 64, 1, 1) SGB_TMA_CASE(64, 64, 1, 1) SGB_TMA_CASE(128, 64, 1, 1)        // stride 2: 64-byte K blocks, one tile per stage
 #undef SGB_TMA_CASE
   set_error("conv_tma: no kernel for this (BN, KB, GT)");
   return 1;
