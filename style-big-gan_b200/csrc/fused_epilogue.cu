@@ -14,6 +14,27 @@
 #include "common.cuh"
 
 namespace sgb {
+// Blocks of `kern` (256 threads, no dynamic shared memory) that are resident on the whole GPU at once.  The one-pass kernels
+// below give every image a whole number of blocks; asking for "4 per SM" when the register count only lets 2 be resident made
+// a grid of 2.05 waves run as three rounds (fused_epilogue_bwd at 0.64 of the copy rate, profiles/README.md).  The grid is
+// sized to ONE resident wave, rounded DOWN per image.
+template <class K>
+static int64_t resident_blocks(K kern) {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0) != cudaSuccess || occ < 1) { (void)cudaGetLastError(); occ = 2; }
+  return (int64_t)occ * num_sms();
+}
+// blocks per image: floor(resident / n), at least 1, at most one pixel lane per block row
+static inline int64_t blocks_per_image(int64_t resident, int n, int64_t hw, int lanes) {
+  int64_t want = resident / (n > 0 ? n : 1);
+  const int64_t maxb = (hw + lanes - 1) / lanes;
+  if (want > maxb) want = maxb;
+  if (want < 1) want = 1;
+  return want;
+}
+}  // namespace sgb
+
+namespace sgb {
 
 struct FusedBwdParams {
   const void* dy; const void* y; void* dconv;
@@ -52,6 +73,12 @@ __global__ void __launch_bounds__(256) fused_epilogue_bwd_kernel(FusedBwdParams 
 #pragma unroll
   for (int j = 0; j < VEC; j++) { accb[j] = 0.f; accs[j] = 0.f; }
   const int64_t img = (int64_t)n * p.hw;
+  // lanes that share a pixel: cvt of them when cvt is a power of two <= 32 (one group = one pixel), else 32 when cvt is a
+  // multiple of 32 (a warp = 32 channel vectors of one pixel); otherwise no shuffle reduction
+  const bool cvt_pow2 = (cvt & (cvt - 1)) == 0;
+  const int grp = (cvt_pow2 && cvt <= 32) ? cvt : 32;
+  const bool grp_shfl = cvt_pow2;                         // power of two: <= 32 -> groups inside a warp, > 32 -> whole warps
+  const unsigned gmask = grp >= 32 ? 0xffffffffu : (((1u << grp) - 1u) << ((threadIdx.x & 31) & ~(grp - 1)));
   if (active) {
     constexpr int U = 4;                                  // pixels in flight per thread (loads issued before the maths)
     for (int px0 = p0 + pl; px0 < p1; px0 += U * lanes) {
@@ -87,7 +114,19 @@ __global__ void __launch_bounds__(256) fused_epilogue_bwd_kernel(FusedBwdParams 
           out.v[j] = from_acc<T>(dz * sc[j]);
         }
         st_stream((uint4*)p.dconv + v, out.raw);
-        if (p.dnoise) atomicAdd(p.dnoise + img + px, dn);
+        if (p.dnoise) {
+          // the cvt threads of a pixel are consecutive lanes with the same trip count: reduce over them with shuffles (group
+          // mask), then ONE access per pixel and warp (it was one atomic per thread: 16-way contention at 64 fp32 channels)
+          if (grp_shfl) {
+            for (int o = grp >> 1; o > 0; o >>= 1) dn += __shfl_xor_sync(gmask, dn, o);
+            if ((cv & (grp - 1)) == 0) {
+              if (cvt <= 32) p.dnoise[img + px] = dn;                 // the whole pixel is in this group
+              else atomicAdd(p.dnoise + img + px, dn);
+            }
+          } else {
+            atomicAdd(p.dnoise + img + px, dn);
+          }
+        }
       }
     }
   }
@@ -137,10 +176,9 @@ extern "C" int sgb_fused_epilogue_bwd(const void* dy, const void* y, void* dconv
   p.alpha = (act == SGB_ACT_LINEAR) ? 1.f : alpha; p.gain = gain; p.clamp = clamp;
   // ~4 blocks per SM in total, whole blocks inside one image
   const int cvt = c / vec, lanes = 256 / cvt;
-  int64_t want = ((int64_t)num_sms() * 4 + n - 1) / n;               // blocks per image
-  int64_t maxb = ((int64_t)hw + lanes - 1) / lanes;                // at least one pixel per lane
-  if (want > maxb) want = maxb;
-  if (want < 1) want = 1;
+  static const int64_t res_f32 = resident_blocks(fused_epilogue_bwd_kernel<float>), res_f16 = resident_blocks(fused_epilogue_bwd_kernel<__half>),
+                       res_bf16 = resident_blocks(fused_epilogue_bwd_kernel<__nv_bfloat16>);
+  const int64_t want = blocks_per_image(dtype == SGB_F32 ? res_f32 : (dtype == SGB_F16 ? res_f16 : res_bf16), n, hw, lanes);
   p.ppb = (int)(((int64_t)hw + want - 1) / want);
   p.blocks_per_img = (hw + p.ppb - 1) / p.ppb;
   const int64_t grid = (int64_t)n * p.blocks_per_img;
@@ -163,37 +201,57 @@ struct TailParams {
   const void* x; void* y; const void* bias; const float* out_scale; const float* noise;
   int n, c; int64_t hw;
   float alpha, gain, clamp;
+  int ppb, blocks_per_img;      // pixels per block (inside one image) / blocks per image
 };
 
 template <class T>
 __global__ void __launch_bounds__(256) scale_bias_act_kernel(TailParams p) {
+  // thread -> (channel vector cv = tid % cvt, pixel lane pl = tid / cvt) of a chunk of ONE image: the scale and bias of its
+  // channels are registers, the index arithmetic is 32-bit and division-free in the loop, four 16-byte loads are in flight per
+  // thread.  (The first version decoded every vector with two 64-bit divisions and fetched scale / bias per element: 0.62 of
+  // the copy rate in the step, profiles/README.md.)
   constexpr int VEC = Vec16<T>::N;
-  const int64_t cv = p.c / VEC;
-  const int64_t nv = (int64_t)p.n * p.hw * cv;
-  const float e_clamp = p.clamp >= 0.f ? p.clamp : __int_as_float(0x7f800000);
-  for (int64_t v0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v0 < nv; v0 += (int64_t)gridDim.x * blockDim.x * 2) {
-    const int64_t v1 = v0 + (int64_t)gridDim.x * blockDim.x;
-    Vec16<T> in0, in1;
-    in0.raw = ld_stream((const uint4*)p.x + v0);
-    if (v1 < nv) in1.raw = ld_stream((const uint4*)p.x + v1);
+  const int cvt = p.c / VEC;
+  const int lanes = 256 / cvt;
+  const int cv = threadIdx.x % cvt, pl = threadIdx.x / cvt;
+  if (pl >= lanes) return;
+  const int n = blockIdx.x / p.blocks_per_img;
+  const int p0 = (blockIdx.x - n * p.blocks_per_img) * p.ppb;
+  const int p1 = ((int64_t)p0 + p.ppb < p.hw) ? p0 + p.ppb : (int)p.hw;
+  const int c0 = cv * VEC;
+  float sc[VEC], bs[VEC];
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
-      const int64_t v = u ? v1 : v0;
-      if (v >= nv) break;
-      const Vec16<T>& in = u ? in1 : in0;
-      const int64_t pix = v / cv; const int c0 = (int)(v - pix * cv) * VEC; const int64_t n = pix / p.hw;
-      const float nz = p.noise ? p.noise[pix] : 0.f;
+  for (int j = 0; j < VEC; j++) {
+    sc[j] = p.out_scale ? p.out_scale[(int64_t)n * p.c + c0 + j] : 1.f;
+    bs[j] = p.bias ? to_acc<T>(((const T*)p.bias)[c0 + j]) : 0.f;
+  }
+  const float e_clamp = p.clamp >= 0.f ? p.clamp : __int_as_float(0x7f800000);
+  const int64_t img = (int64_t)n * p.hw;
+  constexpr int U = 4;
+  for (int px0 = p0 + pl; px0 < p1; px0 += U * lanes) {
+    Vec16<T> in[U];
+    float nz[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int px = px0 + u * lanes;
+      if (px < p1) {
+        in[u].raw = ld_stream((const uint4*)p.x + (img + px) * cvt + cv);
+        nz[u] = p.noise ? p.noise[img + px] : 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int px = px0 + u * lanes;
+      if (px >= p1) break;
       Vec16<T> out;
 #pragma unroll
       for (int j = 0; j < VEC; j++) {
-        const float sc = p.out_scale ? __ldg(p.out_scale + n * p.c + c0 + j) : 1.f;
-        const float b = p.bias ? to_acc<T>(((const T*)p.bias)[c0 + j]) : 0.f;
-        float t = fmaf(to_acc<T>(in.v[j]), sc, nz + b);
+        float t = fmaf(to_acc<T>(in[u].v[j]), sc[j], nz[u] + bs[j]);
         t = (t > 0.f ? t : t * p.alpha) * p.gain;                       // explicit compares: a NaN pre-activation stays NaN, as in
         t = t < -e_clamp ? -e_clamp : (t > e_clamp ? e_clamp : t);      // bias_act.cu and torch.clamp (fmaxf / fminf drop NaN operands)
         out.v[j] = from_acc<T>(t);
       }
-      st_stream((uint4*)p.y + v, out.raw);
+      st_stream((uint4*)p.y + (img + px) * cvt + cv, out.raw);
     }
   }
 }
@@ -210,8 +268,16 @@ extern "C" int sgb_scale_bias_act(const void* x, const void* bias, const void* o
   sgb::TailParams p;
   p.x = x; p.y = y; p.bias = bias; p.out_scale = (const float*)out_scale; p.noise = (const float*)noise;
   p.n = n; p.c = c; p.hw = hw; p.alpha = (act == SGB_ACT_LINEAR) ? 1.f : alpha; p.gain = gain; p.clamp = clamp;
-  const int64_t nv = (int64_t)n * hw * (c / vec);
-  int64_t blocks = sgb::ceil_div(nv, 512); if (blocks > sgb::num_sms() * 8) blocks = sgb::num_sms() * 8;
+  SGB_REQUIRE(c / vec <= 256, "at most 256 channel vectors");
+  // ~8 blocks per SM in total, whole blocks inside one image
+  const int cvt = c / vec, lanes = 256 / cvt;
+  static const int64_t res_f32 = sgb::resident_blocks(sgb::scale_bias_act_kernel<float>), res_f16 = sgb::resident_blocks(sgb::scale_bias_act_kernel<__half>),
+                       res_bf16 = sgb::resident_blocks(sgb::scale_bias_act_kernel<__nv_bfloat16>);
+  const int64_t want = sgb::blocks_per_image(dtype == SGB_F32 ? res_f32 : (dtype == SGB_F16 ? res_f16 : res_bf16), n, hw, lanes);
+  p.ppb = (int)(((int64_t)hw + want - 1) / want);
+  p.blocks_per_img = (int)((hw + p.ppb - 1) / p.ppb);
+  const int64_t blocks = (int64_t)n * p.blocks_per_img;
+  SGB_REQUIRE(blocks <= 0x7fffffff, "grid too large");
   cudaStream_t s = (cudaStream_t)stream;
   switch (dtype) {
     case SGB_F32:  sgb::scale_bias_act_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(p); break;
@@ -302,10 +368,9 @@ extern "C" int sgb_mod_bwd(const void* g, const void* x, const void* s, void* gx
   sgb::ModBwdParams p;
   p.g = g; p.x = x; p.s = (const float*)s; p.gx = gx; p.gs = (float*)gs; p.n = n; p.c = c; p.hw = hw;
   const int cvt = c / vec, lanes = 256 / cvt;
-  int64_t want = ((int64_t)sgb::num_sms() * 4 + n - 1) / n;
-  int64_t maxb = ((int64_t)hw + lanes - 1) / lanes;
-  if (want > maxb) want = maxb;
-  if (want < 1) want = 1;
+  static const int64_t res_f32 = sgb::resident_blocks(sgb::mod_bwd_kernel<float>), res_f16 = sgb::resident_blocks(sgb::mod_bwd_kernel<__half>),
+                       res_bf16 = sgb::resident_blocks(sgb::mod_bwd_kernel<__nv_bfloat16>);
+  const int64_t want = sgb::blocks_per_image(dtype == SGB_F32 ? res_f32 : (dtype == SGB_F16 ? res_f16 : res_bf16), n, hw, lanes);
   p.ppb = (int)(((int64_t)hw + want - 1) / want);
   p.blocks_per_img = (hw + p.ppb - 1) / p.ppb;
   const int64_t grid = (int64_t)n * p.blocks_per_img;

@@ -634,10 +634,9 @@ __global__ void __launch_bounds__(256, 2) fir_sep_strip_kernel(FirSepParams p) {
 // with 45 % of the issue slots busy and 22 % of the warp slots occupied -- latency-bound.  Here every thread owns NIX private
 // 16-byte slots in each of four stages and issues the cp.async of row k + 3 before it filters row k (zero fill outside the
 // image, so there are no edge branches); the slots are thread-private, so cp.async.wait_group is the only synchronisation.
-template <class T>
+template <class T, int PX>
 __global__ void __launch_bounds__(256, 2) fir_sep_strip_pf_kernel(FirSepParams p) {
   constexpr int VEC = Vec16<T>::N;
-  constexpr int PX = 2;
   constexpr int NIX = PX + 3;
   constexpr int ST = 4;                     // stages = the unroll of the row loop, so the stage index is static
   extern __shared__ __align__(16) uint4 fir_sm[];          // [ST][NIX][256]
@@ -866,19 +865,25 @@ extern "C" int sgb_upfirdn2d_sep(const void* x, const float* fx, const float* fy
   SGB_REQUIRE(gy <= 65535 && gz <= 65535, "grid too large");
   dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)gz), block(cvb, p.xgs);
   cudaStream_t s = (cudaStream_t)stream;
-  // SGB_FIR_PF=0: 16-bit tensors on the register kernel as well (A/B)
-  static const int use_pf = [] { const char* e = getenv("SGB_FIR_PF"); return e ? atoi(e) : 1; }();
-  constexpr int PF_SMEM = 4 * 5 * 256 * 16;
-  if (dtype == SGB_F32) fir_sep_strip_kernel<float><<<grid, block, 0, s>>>(p);
+  // SGB_FIR_PF: 0 = register kernel for every type (A/B), 1 = prefetching kernel for 16-bit tensors only, 2 (default) = for
+  // fp32 tensors as well (PX = 4: 7 slots x 4 stages = 112 KB per CTA, two CTAs still fit an SM).  Measured (r2_run28.sh,
+  // r2_run30.sh): fp16 [4,32,1025,1025] 3.30 -> 4.91 TB/s, fp32 [8,64,257,257] 5.13 -> 5.97 TB/s (0.91 of the copy rate),
+  // ffhq256 step 69.5 -> 68.2 ms
+  static const int use_pf = [] { const char* e = getenv("SGB_FIR_PF"); return e ? atoi(e) : 2; }();
+  constexpr int PF_SMEM = 4 * 5 * 256 * 16, PF_SMEM32 = 4 * 7 * 256 * 16;
+  if (dtype == SGB_F32 && use_pf >= 2) {
+    SGB_SET_MAX_SMEM((fir_sep_strip_pf_kernel<float, 4>), PF_SMEM32);
+    fir_sep_strip_pf_kernel<float, 4><<<grid, block, PF_SMEM32, s>>>(p);
+  } else if (dtype == SGB_F32) fir_sep_strip_kernel<float><<<grid, block, 0, s>>>(p);
   else if (!use_pf) {
     if (dtype == SGB_F16) fir_sep_strip_kernel<__half><<<grid, block, 0, s>>>(p);
     else fir_sep_strip_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(p);
   } else if (dtype == SGB_F16) {
-    SGB_SET_MAX_SMEM(fir_sep_strip_pf_kernel<__half>, PF_SMEM);
-    fir_sep_strip_pf_kernel<__half><<<grid, block, PF_SMEM, s>>>(p);
+    SGB_SET_MAX_SMEM((fir_sep_strip_pf_kernel<__half, 2>), PF_SMEM);
+    fir_sep_strip_pf_kernel<__half, 2><<<grid, block, PF_SMEM, s>>>(p);
   } else {
-    SGB_SET_MAX_SMEM(fir_sep_strip_pf_kernel<__nv_bfloat16>, PF_SMEM);
-    fir_sep_strip_pf_kernel<__nv_bfloat16><<<grid, block, PF_SMEM, s>>>(p);
+    SGB_SET_MAX_SMEM((fir_sep_strip_pf_kernel<__nv_bfloat16, 2>), PF_SMEM);
+    fir_sep_strip_pf_kernel<__nv_bfloat16, 2><<<grid, block, PF_SMEM, s>>>(p);
   }
   SGB_LAUNCH_CHECK();
   return 0;
