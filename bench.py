@@ -198,6 +198,8 @@ def main():
     ap.add_argument('--no-strict', action='store_true', help='skip the strict-fp32 (reference default arithmetic) run')
     ap.add_argument('--no-callers', action='store_true', help="skip the runs of the reference's unchanged callers (sgb200 / reference GPU path)")
     ap.add_argument('--lean', action='store_true', help='only the headline measurement (ncu launch-list runs)')
+    ap.add_argument('--start-idx', type=int, default=0, help='iteration index the timed loop starts at (ncu launch lists: 1 = an '
+                    'iteration with the main phases only; the default 0 = whole lazy-regularisation periods)')
     args = ap.parse_args()
 
     if args.lean:
@@ -315,7 +317,7 @@ def measure(ctx, args, workload, fp32_mode, steps, e2e, roofline, clocks, breakd
 
     def timed_loop(nsteps, from_host, profile):
         """returns (ms max over ranks, launches, profile summary or None, last losses)"""
-        tr.batch_idx = 0
+        tr.batch_idx = args.start_idx
         barrier()
         if profile:
             _lib.profile_start()

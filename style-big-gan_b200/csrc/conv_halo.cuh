@@ -165,8 +165,9 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(HaloParams p
     // image / virtual row of that tile's first patch row, refreshed once per tile (the 64-bit divisions of decode_tile were
     // ~15 % of the producers' samples when they ran once per K block: profiles/README.md, small 512-channel layers)
     int pub_n0 = 0, pub_rem0 = 0;
+    const bool need_pass = scb || (KIND == 2 && !(p.debug & 64));      // 16-bit tensors without a style scale: publish() touches nothing
     auto pub_decode = [&]() {
-      if (pub_tile < p.total_tiles) {
+      if (need_pass && pub_tile < p.total_tiles) {
         int nt_, u0o, x0_;
         decode_tile(p, GT, pub_tile, nt_, u0o, x0_);
         pub_n0 = u0o / p.VR; pub_rem0 = u0o - pub_n0 * p.VR;
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_kernel(HaloParams p
       // biased (every operand shrinks by ~2^-11 on average), and the bias compounds over the layers of a network: the
       // deepest gradients of the golden network came out ~2-3 % short.  The producers therefore round the landed patch to
       // TF32 (cvt.rna, what cuDNN's TF32 convolutions amount to) in the same in-place pass that applies the style scale.
-      if (scb || (KIND == 2 && !(p.debug & 64))) {        // SGB_HALO_DEBUG=64: A/B switch, leave the truncation to the MMA
+      if (need_pass) {                                    // SGB_HALO_DEBUG=64: A/B switch, leave the truncation to the MMA
         uint8_t* dst = a_base + sa * p.a_stage_bytes;
         const int co = pub_tile_cb * BK + j * TC;
         if (co < d.ci) {

@@ -6,6 +6,7 @@
 // activity, ~1.1 TB/s); here a thread owns one pixel, streams its channels_last row of x with 16-byte loads, and keeps
 // the <= 8 accumulators in registers.  The (style-scaled) weights of the block's sample sit in shared memory and are
 // read as broadcasts.  HBM traffic = x once + y once.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace sgb {
@@ -18,9 +19,14 @@ struct SmallParams {
   int hw;
 };
 
-template <class T, int CO>
+// G threads share a pixel: thread g of the group loads the 16-byte chunks g, g + G, ... of the pixel's channel row, so the G
+// lanes of a group read G * 16 contiguous bytes per step (G = 8: one 128-byte line; with one thread per pixel every load
+// instruction of a warp touched 32 different rows, 16 bytes of each 32-byte sector: 0.39 of the copy rate in the step), and the
+// CO partial sums are combined with group shuffles.  G = 1 is the original one-thread-per-pixel form (few channels).
+template <class T, int CO, int G>
 __global__ void __launch_bounds__(SMALL_THREADS) conv1x1_small_kernel(SmallParams p) {
   constexpr int TC = 16 / sizeof(T);
+  constexpr int PB = SMALL_THREADS / G;                  // pixels per block
   extern __shared__ float wsm[];                         // [CO][ci], scaled by the sample's style
   const sgb_conv_desc& d = p.d;
   const int n = blockIdx.y;
@@ -33,15 +39,16 @@ __global__ void __launch_bounds__(SMALL_THREADS) conv1x1_small_kernel(SmallParam
     wsm[i] = sc ? v * sc[c] : v;
   }
   __syncthreads();
-  const int pix = blockIdx.x * SMALL_THREADS + threadIdx.x;
-  if (pix >= p.hw) return;
+  const int g = threadIdx.x % G;
+  const int pix = blockIdx.x * PB + threadIdx.x / G;
+  if (pix >= p.hw) return;                               // the whole group leaves together (group-mask shuffles below)
   const int h = pix / d.in_w, wq = pix - h * d.in_w;
   const T* xp = (const T*)p.x + (int64_t)n * d.x_strides[0] + (int64_t)h * d.x_strides[2] + (int64_t)wq * d.x_strides[3];
   float acc[CO];
 #pragma unroll
   for (int o = 0; o < CO; o++) acc[o] = 0.f;
 #pragma unroll 4
-  for (int c = 0; c < d.ci; c += TC) {
+  for (int c = g * TC; c < d.ci; c += G * TC) {
     Vec16<T> v;
     v.raw = __ldg((const uint4*)(xp + c));
 #pragma unroll
@@ -52,6 +59,14 @@ __global__ void __launch_bounds__(SMALL_THREADS) conv1x1_small_kernel(SmallParam
         acc[o] += to_acc<T>(v.v[q]) * w4.x + to_acc<T>(v.v[q + 1]) * w4.y + to_acc<T>(v.v[q + 2]) * w4.z + to_acc<T>(v.v[q + 3]) * w4.w;
       }
     }
+  }
+  if (G > 1) {
+    const unsigned gmask = (G >= 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
+#pragma unroll
+    for (int off = G >> 1; off > 0; off >>= 1)
+#pragma unroll
+      for (int o = 0; o < CO; o++) acc[o] += __shfl_xor_sync(gmask, acc[o], off);
+    if (g != 0) return;
   }
   T* yp = (T*)p.y + (int64_t)n * d.y_strides[0] + (int64_t)h * d.y_strides[2] + (int64_t)wq * d.y_strides[3];
 #pragma unroll
@@ -77,9 +92,19 @@ template <class T>
 static int launch_small(const sgb_conv_desc* d, const void* x, const void* w, void* y, cudaStream_t s) {
   SmallParams p; p.d = *d; p.x = x; p.w = w; p.y = y; p.hw = d->in_h * d->in_w;
   SGB_REQUIRE(aligned16(x), "x must be 16-byte aligned");
-  const dim3 grid((unsigned)ceil_div(p.hw, SMALL_THREADS), (unsigned)d->n);
-  if (d->co <= 4) conv1x1_small_kernel<T, 4><<<grid, SMALL_THREADS, sizeof(float) * 4 * d->ci, s>>>(p);
-  else conv1x1_small_kernel<T, 8><<<grid, SMALL_THREADS, sizeof(float) * 8 * d->ci, s>>>(p);
+  constexpr int TC = 16 / sizeof(T);
+  // SGB_SMALL_G=1: one thread per pixel everywhere (A/B)
+  static const int env_g = [] { const char* e = getenv("SGB_SMALL_G"); return e ? atoi(e) : 8; }();
+  const bool grouped = env_g >= 8 && d->ci >= 8 * TC;            // at least one chunk per lane of a group of 8
+  const int pb = grouped ? SMALL_THREADS / 8 : SMALL_THREADS;
+  const dim3 grid((unsigned)ceil_div(p.hw, pb), (unsigned)d->n);
+  if (grouped) {
+    if (d->co <= 4) conv1x1_small_kernel<T, 4, 8><<<grid, SMALL_THREADS, sizeof(float) * 4 * d->ci, s>>>(p);
+    else conv1x1_small_kernel<T, 8, 8><<<grid, SMALL_THREADS, sizeof(float) * 8 * d->ci, s>>>(p);
+  } else {
+    if (d->co <= 4) conv1x1_small_kernel<T, 4, 1><<<grid, SMALL_THREADS, sizeof(float) * 4 * d->ci, s>>>(p);
+    else conv1x1_small_kernel<T, 8, 1><<<grid, SMALL_THREADS, sizeof(float) * 8 * d->ci, s>>>(p);
+  }
   SGB_LAUNCH_CHECK();
   return 0;
 }
