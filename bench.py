@@ -217,6 +217,9 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device('cuda', local_rank)
     if world > 1:
+        # the in-graph gradient all-reduce (~120 MB per phase): more NCCL channels than its default for a message of this size
+        # (measured on 2 B200s, benchmarks/gpu_runs/r2_run38.sh: 69.77 -> 69.38 ms per step); an explicit setting wins
+        os.environ.setdefault('NCCL_MIN_NCHANNELS', '32')
         dist.init_process_group('nccl', device_id=device)
     assert world == args.gpus or world == 1, f'--gpus {args.gpus} but WORLD_SIZE={world}'
     _lib.lib()     # fail loudly if the CUDA library is missing

@@ -93,8 +93,10 @@ static int launch_small(const sgb_conv_desc* d, const void* x, const void* w, vo
   SmallParams p; p.d = *d; p.x = x; p.w = w; p.y = y; p.hw = d->in_h * d->in_w;
   SGB_REQUIRE(aligned16(x), "x must be 16-byte aligned");
   constexpr int TC = 16 / sizeof(T);
-  // SGB_SMALL_G=1: one thread per pixel everywhere (A/B)
-  static const int env_g = [] { const char* e = getenv("SGB_SMALL_G"); return e ? atoi(e) : 8; }();
+  // SGB_SMALL_G=8: eight lanes per pixel.  Measured level with one thread per pixel (r2_run37.sh: 1.48 vs 1.38 ms per step for the
+  // family, step 68.75 vs 68.68 ms) -- the half-used sectors of the one-thread form are served by L1 on the next load -- so the
+  // simpler form stays the default
+  static const int env_g = [] { const char* e = getenv("SGB_SMALL_G"); return e ? atoi(e) : 1; }();
   const bool grouped = env_g >= 8 && d->ci >= 8 * TC;            // at least one chunk per lane of a group of 8
   const int pb = grouped ? SMALL_THREADS / 8 : SMALL_THREADS;
   const dim3 grid((unsigned)ceil_div(p.hw, pb), (unsigned)d->n);

@@ -169,3 +169,27 @@ def test_reference_training_iterations_run(H):
     assert seen[0] == ['Gmain', 'Dmain', 'Dreg'] and seen[1] == ['Gmain', 'Dmain'] and seen[4] == ['Gmain', 'Dmain', 'Dreg']
     assert all(torch.isfinite(p).all() for p in list(tr.G.parameters()) + list(tr.D.parameters()))
     assert any((a != b.detach()).any() for a, b in zip(p0, tr.G.parameters()))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# ADA AugmentPipe: the reference's unchanged train_parts/augmentations.py:121-432 on the sgb200 ops.
+# It reaches the ops in forms the networks never use: 12-tap sym6 separable upsample2d / downsample2d with negative padding and
+# flip_filter (:294,305), grid_sample_gradfix (:302) and the per-sample depthwise filter bank conv2d(groups = N * C) (:402-403).
+# With debug_percentile and p = 1 the pipe is deterministic; golden = the same class on the reference's CPU path
+# (oracle/make_golden_augment.py -> tests/golden/augment_pipe.npz).
+def test_reference_augment_pipe_on_sgb200(H):
+    from oracle import make_golden_augment as MG
+    import train_parts.augmentations as aug_mod
+    import sgb200.ops as ops
+    assert aug_mod.upfirdn2d is ops.upfirdn2d and aug_mod.conv2d_gradfix is ops.conv2d_gradfix
+    z = np.load(os.path.join(GOLDEN, 'augment_pipe.npz'))
+    from sgb200 import _lib
+    with _tf32(False):
+        for case in MG.CASES:
+            n0 = _lib.launch_count()
+            images, out, gi, _ = MG.run_case(aug_mod, case, device=DEV)
+            assert _lib.launch_count() > n0, 'AugmentPipe did not reach libsgb200'
+            assert np.array_equal(images.cpu().numpy(), z[case['name'] + '.images'])
+            # bilinear grid_sample + 12-tap filters in fp32: the CPU and CUDA arithmetic differ in summation order only
+            assert_close(out, torch.from_numpy(z[case['name'] + '.out']), 2e-4, f"AugmentPipe {case['name']} forward")
+            assert_close(gi, torch.from_numpy(z[case['name'] + '.grad_images']), 5e-4, f"AugmentPipe {case['name']} d/d images")
