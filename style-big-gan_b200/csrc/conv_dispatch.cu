@@ -1,5 +1,6 @@
-// C-ABI entry points for convolution: validation + routing between the tcgen05 implicit-GEMM kernels
-// (conv_umma.cu) and the shape-complete SIMT kernels (conv_simt.cu).
+// C-ABI entry points for convolution: validation + routing between the tcgen05 implicit-GEMM kernels (conv_tma.cuh: TMA-staged
+// stride 1; conv_halo.cuh: every other geometry up to 3 x 3; conv_umma.cu: per-tap fallback; conv_wgrad_*.cu: weight gradient),
+// the small-output 1 x 1 bandwidth kernel (conv_small.cu) and the shape-complete SIMT kernels (conv_simt.cu).
 #include "common.cuh"
 
 namespace sgb {
